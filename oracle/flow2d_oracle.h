@@ -1,0 +1,102 @@
+/*
+ * flow2d_oracle.h -- CPU oracle for the cuda-flow2d hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This is a plain-C, fp32, literal restatement of the reference's ComputeFlow path
+ * (axruff/cuda-flow2d).  It exists to check the sm_100a kernels; it is never linked
+ * into, imported by or called from the product library.  Only tests/, the smoke check
+ * in __graft_entry__.py and bench.py's cpu_baseline leg may use it.
+ *
+ * Parity status: the reference ships no tests, golden vectors or fixtures for this path
+ * (SURVEY.md F6), so this restatement is pinned against the reference's OWN CUDA build
+ * (oracle/_ref, built by oracle/Makefile from the sources under /root/reference and run
+ * on the GPU box): per-kernel, by driving the reference PTX kernels on identical buffers
+ * (oracle/ref_stage.cpp), and end to end on the rub pair (tests/golden/).
+ *
+ * Every function cites the reference file:line it follows.  Floating-point expression
+ * trees (which mul/add pairs are fused) follow the reference kernels as compiled by
+ * nvcc 12.9 -ptx + ptxas -arch=sm_100 (see DESIGN.md "Arithmetic contract").
+ */
+#ifndef FLOW2D_ORACLE_H_
+#define FLOW2D_ORACLE_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORACLE_GREY = 0, ORACLE_GRADIENT = 1 };
+
+typedef struct oracle_params {
+  size_t warp_levels_count;      /* main.cpp:70 */
+  float  warp_scale_factor;      /* main.cpp:71 */
+  size_t outer_iterations_count; /* main.cpp:72 */
+  size_t inner_iterations_count; /* main.cpp:73 */
+  float  equation_alpha;         /* main.cpp:74 */
+  float  equation_smoothness;    /* main.cpp:75 */
+  float  equation_data;          /* main.cpp:76 */
+  size_t median_radius;          /* main.cpp:77 (really the window diameter) */
+  float  gaussian_sigma;         /* main.cpp:78 */
+  int    constancy;              /* data_structs.h:27; ORACLE_GREY | ORACLE_GRADIENT */
+} oracle_params;
+
+/* optical_flow_base_2d.cpp:36-59 */
+size_t oracle_max_warp_level(size_t width, size_t height, float scale_factor);
+/* optical_flow_2d.cpp:268-272 */
+void oracle_level_geometry(size_t W, size_t H, float scale_factor, int level,
+                           size_t* cw, size_t* ch, float* hx, float* hy);
+
+/* cuda_operation_convolution_2d.cpp:83-112; taps must hold 2*radius+1 floats (<= 51). Returns radius. */
+int oracle_gauss_taps(float sigma, float* taps);
+/* convolution_2d.cu:74-261 (zero padding, rows then columns) */
+void oracle_blur(const float* in, float* out, size_t w, size_t h, size_t pitch, float sigma);
+
+/* resample_2d.cu:34-118 + cuda_operation_resample_2d.cpp:99-105 (x pass then y pass) */
+void oracle_resample(const float* in, size_t iw, size_t ih, float* out, size_t ow, size_t oh, size_t pitch);
+/* index part of resample_2d.cu:44-51, exposed for bit-exact index tests */
+void oracle_resample_cells(size_t in_n, size_t out_n, size_t x, int* left_i, int* right_i);
+
+/* registration_2d.cu:34-74 */
+void oracle_warp(const float* f0, const float* f1, const float* u, const float* v,
+                 size_t w, size_t h, size_t pitch, float hx, float hy, float* out);
+
+/* solve_2d.cu:43-198 */
+void oracle_phi_ksi(const float* f0, const float* f1, const float* u, const float* v,
+                    const float* du, const float* dv, size_t w, size_t h, size_t pitch,
+                    float hx, float hy, float e_smooth, float e_data, float* phi, float* ksi);
+/* solve_2d.cu:200-377 (one Jacobi sweep, Grey) */
+void oracle_sweep_grey(const float* f0, const float* f1, const float* u, const float* v,
+                       const float* du, const float* dv, const float* phi, const float* ksi,
+                       size_t w, size_t h, size_t pitch, float hx, float hy, float alpha,
+                       float* du_out, float* dv_out);
+/* solve_2d.cu:683-953 (one Jacobi sweep, Gradient; 16x8 tile replicate artefact emulated, F5) */
+void oracle_sweep_grad(const float* f0, const float* f1, const float* u, const float* v,
+                       const float* du, const float* dv, const float* phi, const float* ksi,
+                       size_t w, size_t h, size_t pitch, float hx, float hy, float alpha,
+                       float* du_out, float* dv_out);
+/* cuda_operation_solve_2d.cpp:106-315: memset du,dv; outer x (phi/ksi + inner x sweep + swap).
+ * du/dv/tmp_du/tmp_dv are caller buffers; the result is left in du, dv (pointer swaps are
+ * resolved by copying). */
+void oracle_solve_level(const float* f0, const float* f1, const float* u, const float* v,
+                        float* du, float* dv, float* phi, float* ksi, float* tmp_du, float* tmp_dv,
+                        size_t w, size_t h, size_t pitch, float hx, float hy,
+                        const oracle_params* p);
+
+/* add_2d.cu:33-46 */
+void oracle_add(float* a, const float* b, size_t w, size_t h, size_t pitch);
+/* median_2d.cu:87-299 + cuda_operation_median_2d.cpp:100-111. Returns 0 if a filter/copy ran,
+ * 1 if the radius is unsupported (the reference then leaves `out` untouched). */
+int oracle_median(const float* in, float* out, size_t w, size_t h, size_t pitch, size_t radius);
+
+/* optical_flow_2d.cpp:142-569: the whole path. f0,f1,u,v are dense W*H row-major. Returns 0. */
+int oracle_compute_flow(const float* f0, const float* f1, size_t W, size_t H,
+                        const oracle_params* p, float* u, float* v);
+
+/* number of OpenMP threads the oracle will use (1 if built without OpenMP) */
+int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
