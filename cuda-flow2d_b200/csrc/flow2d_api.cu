@@ -1,0 +1,558 @@
+// flow2d_api.cu -- handle, level scheduler and the C ABI of include/flow2d.h.
+//
+// Host-side orchestration of the hot path; follows OpticalFlow2D::ComputeFlow
+// (src/optical_flow/optical_flow_2d.cpp:142-569) stage for stage, but everything is enqueued on one
+// stream without any host synchronisation inside the pyramid (the reference blocks on
+// cuStreamSynchronize after every inner sweep, cuda_operation_solve_2d.cpp:291).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/flow2d.h"
+#include "kernels.h"
+
+using namespace flow2d;
+
+namespace {
+
+constexpr int kPitchAlign = 128;  // floats; = the 512-byte pitch granularity the reference gets from cuMemAllocPitch
+
+enum Container {
+  C_IN0, C_IN1,        // uploaded frames
+  C_BLUR0, C_BLUR1,    // presmoothed frames
+  C_RES0, C_RES1,      // frames resampled to the current level
+  C_WARPED,            // frame 1 registered by the current flow
+  C_U, C_V, C_U2, C_V2,
+  C_DU0, C_DV0, C_DU1, C_DV1,
+  C_PHI, C_KSI,
+  C_FX, C_FY, C_FT,
+  C_TMP0, C_TMP1,      // x-pass results of the resampler
+  C_OUT_U, C_OUT_V,    // final flow of flow2d_compute (host API)
+  C_J0, C_J1, C_J2, C_J3, C_J4,  // gradient mode only
+  C_COUNT
+};
+
+}  // namespace
+
+struct flow2d_handle {
+  int device = 0;
+  size_t W = 0, H = 0, pitch = 0;  // pitch in floats
+  int constancy = FLOW2D_GREY;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  float* pool = nullptr;
+  float* c[C_COUNT] = {};
+  long long launches = 0;
+  int levels_run = 0;
+  float device_ms = 0.f;
+  std::string err;
+};
+
+namespace {
+
+int fail(flow2d_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    h->err = buf;
+  }
+  return code;
+}
+
+#define CU_TRY(h, call)                                                                        \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail((h), FLOW2D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+
+int check_launch(flow2d_handle* h, const char* what, int kernels) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, FLOW2D_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  h->launches += kernels;
+  return FLOW2D_OK;
+}
+
+#define TRY(expr)              \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != FLOW2D_OK) return rc_; \
+  } while (0)
+
+// cuda_operation_convolution_2d.cpp:83-112
+int gauss_taps(flow2d_handle* h, float sigma, GaussTaps* t) {
+  const float pixel_size = 1.0f;
+  const size_t precision = 3;
+  const size_t radius = (size_t)((float)precision * sigma / pixel_size);
+  if (radius > (size_t)kMaxGaussRadius)
+    return fail(h, FLOW2D_ERR_UNSUPPORTED, "gaussian_sigma %g needs a kernel radius of %zu > %d", (double)sigma, radius,
+                kMaxGaussRadius);
+  const int r = (int)radius;
+  t->radius = r;
+  for (int i = -r; i <= r; i++) {
+    const float arg = -((float)(i * i) * pixel_size * pixel_size);
+    t->c[i + r] = (float)(1.0 / ((double)sigma * std::sqrt(2.0 * 3.1415926)) *
+                          std::exp((double)arg / (2.0 * (double)sigma * (double)sigma)));
+  }
+  float sum = 0.0f;
+  for (int i = 0; i < 2 * r + 1; i++) sum = sum + t->c[i];
+  for (int i = 0; i < 2 * r + 1; i++) t->c[i] = t->c[i] / sum;
+  return FLOW2D_OK;
+}
+
+// cuda_operation_median_2d.cpp:100-111 -> 1, 3, 5, 7 or an error
+int normalise_median(flow2d_handle* h, size_t radius, int* out) {
+  const size_t asked = radius;
+  if (radius == 1) {  // copy; tested before the even-value rule, like upstream
+    *out = 1;
+    return FLOW2D_OK;
+  }
+  if (radius % 2 == 0 && radius > 0) radius -= 1;
+  if (radius == 3 || radius == 5 || radius == 7) {
+    *out = (int)radius;
+    return FLOW2D_OK;
+  }
+  radius = asked;
+  return fail(h, FLOW2D_ERR_UNSUPPORTED, "median_radius %zu is not supported (1 = off, 3, 5, 7; even values are decremented)",
+              radius);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_level(flow2d_handle* h, size_t w, size_t hh) {
+  if (w < 2 || hh < 2 || w > h->W || hh > h->H)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "level size %zux%zu outside [2x2, %zux%zu]", w, hh, h->W, h->H);
+  return FLOW2D_OK;
+}
+
+LevelGeom geom(const flow2d_handle* h, size_t w, size_t hh, float hx, float hy) {
+  LevelGeom g;
+  g.w = (int)w; g.h = (int)hh; g.pitch = (int)h->pitch; g.hx = hx; g.hy = hy;
+  return g;
+}
+
+// CudaOperationSolve2D::Execute (cuda_operation_solve_2d.cpp:229-299) on top of solve_pass.
+// The result is left in du_a/dv_a; du_b/dv_b are scratch.  fx,fy,ft (and J in gradient mode) must
+// hold the derivative planes of this level.
+int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float* v, float* du_a, float* dv_a,
+              float* du_b, float* dv_b, float* phi, float* ksi, bool want_phi, const flow2d_params* p) {
+  const int outer = (int)p->outer_iterations_count, inner = (int)p->inner_iterations_count;
+  if (outer == 0 || inner == 0) {
+    // no sweep runs: the increment stays at its initial zero (cuda_operation_solve_2d.cpp:229-232)
+    CU_TRY(h, cudaMemset2DAsync(du_a, h->pitch * 4, 0, (size_t)g.w * 4, g.h, h->stream));
+    CU_TRY(h, cudaMemset2DAsync(dv_a, h->pitch * 4, 0, (size_t)g.w * 4, g.h, h->stream));
+    return FLOW2D_OK;
+  }
+  const bool grad = h->constancy == FLOW2D_GRADIENT;
+  SolveArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.fx = h->c[C_FX]; a.fy = h->c[C_FY]; a.ft = h->c[C_FT];
+  for (int i = 0; i < 5; i++) a.J[i] = h->c[C_J0 + i];
+  a.u = u; a.v = v;
+  a.w = g.w; a.h = g.h; a.pitch = g.pitch;
+  a.hx = g.hx; a.hy = g.hy;
+  a.alpha = p->equation_alpha; a.e_smooth = p->equation_smoothness; a.e_data = p->equation_data;
+
+  // resident mode: the whole level (plus a one-cell apron) fits one CTA's region
+  const bool fits = g.w + 4 + 1 <= kSolveLW && g.h + 1 + 1 <= kSolveLH;
+  if (fits && p->resident_levels >= 0) {
+    a.du_in = a.dv_in = nullptr;
+    a.phi_in = a.ksi_in = nullptr;
+    a.du_out = du_a; a.dv_out = dv_a;
+    a.phi_out = want_phi ? phi : nullptr; a.ksi_out = want_phi ? ksi : nullptr;
+    a.sweeps = inner; a.outer = outer;
+    a.ow = kSolveLW; a.oh = kSolveLH; a.halo_x = 4; a.halo_y = 1;
+    launch_solve_pass(h->stream, a, grad, 1, 1);
+    return check_launch(h, "solve_pass(resident)", 1);
+  }
+
+  int S = p->sweeps_per_pass > 0 ? p->sweeps_per_pass : 5;
+  if (S > FLOW2D_MAX_SWEEPS_PER_PASS) S = FLOW2D_MAX_SWEEPS_PER_PASS;
+  const int npass = (inner + S - 1) / S;
+  const long long total = (long long)outer * npass;
+  float* bufs[2][2] = {{du_a, dv_a}, {du_b, dv_b}};
+  long long pass = 0;
+  const float *cur_du = nullptr, *cur_dv = nullptr;
+  a.outer = 1;
+  for (int o = 0; o < outer; ++o) {
+    int left = inner;
+    for (int q = 0; q < npass; ++q, ++pass) {
+      const int s = (left + (npass - q) - 1) / (npass - q);  // spread the sweeps evenly over the passes
+      left -= s;
+      const int dst = (int)((total - 1 - pass) & 1);  // the last pass writes buffer 0 = du_a/dv_a
+      a.du_in = cur_du; a.dv_in = cur_dv;
+      a.du_out = bufs[dst][0]; a.dv_out = bufs[dst][1];
+      const bool first = (q == 0);
+      a.phi_in = first ? nullptr : phi; a.ksi_in = first ? nullptr : ksi;
+      const bool store_phi = first && (npass > 1 || (want_phi && o == outer - 1));
+      a.phi_out = store_phi ? phi : nullptr; a.ksi_out = store_phi ? ksi : nullptr;
+      a.sweeps = s;
+      a.halo_y = s + 1;
+      a.halo_x = (s + 1 <= 4) ? 4 : 8;
+      a.ow = kSolveLW - 2 * a.halo_x;
+      a.oh = kSolveLH - 2 * a.halo_y;
+      launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (g.h + a.oh - 1) / a.oh);
+      TRY(check_launch(h, "solve_pass", 1));
+      cur_du = a.du_out; cur_dv = a.dv_out;
+    }
+  }
+  return FLOW2D_OK;
+}
+
+int run_derivatives(flow2d_handle* h, const LevelGeom& g, const float* f0, const float* f1w) {
+  launch_derivatives(h->stream, f0, f1w, h->c[C_FX], h->c[C_FY], h->c[C_FT], g);
+  TRY(check_launch(h, "derivatives", 1));
+  if (h->constancy == FLOW2D_GRADIENT) {
+    float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
+    launch_grad_tensor(h->stream, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, g);
+    TRY(check_launch(h, "grad_tensor", 1));
+  }
+  return FLOW2D_OK;
+}
+
+int validate_params(flow2d_handle* h, const flow2d_params* p, int* median) {
+  if (!p) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "params is null");
+  if (!(p->warp_scale_factor > 0.f) || !(p->warp_scale_factor < 1.f))
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT,
+                "warp_scale_factor %g must be in (0,1): the reference runs no level at all for >= 1 "
+                "(optical_flow_base_2d.cpp:43-58); use warp_levels_count = 1 for a single level",
+                (double)p->warp_scale_factor);
+  if (p->warp_levels_count < 1) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "warp_levels_count must be >= 1");
+  if (p->sweeps_per_pass < 0 || p->sweeps_per_pass > FLOW2D_MAX_SWEEPS_PER_PASS)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "sweeps_per_pass must be 0..%d", FLOW2D_MAX_SWEEPS_PER_PASS);
+  if (p->outer_iterations_count > 1000000 || p->inner_iterations_count > 1000000)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "iteration counts out of range");
+  return normalise_median(h, p->median_radius, median);
+}
+
+// The pyramid.  frame_0 / frame_1 / out_u / out_v are device containers.
+int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame_1, float* out_u, float* out_v,
+                      const flow2d_params* p) {
+  int median = 1;
+  TRY(validate_params(h, p, &median));
+  const size_t W = h->W, H = h->H;
+  cudaStream_t st = h->stream;
+  h->levels_run = 0;
+
+  // presmoothing (optical_flow_2d.cpp:218-246)
+  const float* frame[2] = {frame_0, frame_1};
+  if (p->gaussian_sigma > 0.0f) {
+    GaussTaps taps;
+    TRY(gauss_taps(h, p->gaussian_sigma, &taps));
+    for (int i = 0; i < 2; i++) {
+      launch_blur(st, frame[i], h->c[C_BLUR0 + i], (int)W, (int)H, (int)h->pitch, taps);
+      TRY(check_launch(h, "blur", 1));
+      frame[i] = h->c[C_BLUR0 + i];
+    }
+  }
+
+  const size_t max_level = flow2d_max_warp_level(W, H, p->warp_scale_factor);
+  int level = (int)(p->warp_levels_count < max_level ? p->warp_levels_count : max_level) - 1;
+  float *u = h->c[C_U], *v = h->c[C_V], *u2 = h->c[C_U2], *v2 = h->c[C_V2];
+  size_t pw = 0, ph = 0;
+
+  while (level >= 0) {
+    size_t cw, ch;
+    float hx, hy;
+    flow2d_level_geometry(W, H, p->warp_scale_factor, level, &cw, &ch, &hx, &hy);
+    const LevelGeom g = geom(h, cw, ch, hx, hy);
+
+    // frames of this level: always restricted from the full-resolution frames (279-305)
+    const float* fr[2] = {frame[0], frame[1]};
+    if (level != 0) {
+      float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP1]};
+      float* res[2] = {h->c[C_RES0], h->c[C_RES1]};
+      launch_resample(st, frame, tmp, res, 2, (int)W, (int)H, g.w, g.h, g.pitch);
+      TRY(check_launch(h, "resample(frames)", 2));
+      fr[0] = res[0]; fr[1] = res[1];
+    }
+    // flow of this level: zero, or prolongated from the previous level (308-341)
+    if (pw == 0) {
+      CU_TRY(h, cudaMemset2DAsync(u, h->pitch * 4, 0, cw * 4, ch, st));
+      CU_TRY(h, cudaMemset2DAsync(v, h->pitch * 4, 0, cw * 4, ch, st));
+    } else {
+      const float* in[2] = {u, v};
+      float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP1]};
+      float* out[2] = {u2, v2};
+      launch_resample(st, in, tmp, out, 2, (int)pw, (int)ph, g.w, g.h, g.pitch);
+      TRY(check_launch(h, "resample(flow)", 2));
+      std::swap(u, u2); std::swap(v, v2);
+    }
+    // backward registration (344-363) and the level's derivative planes
+    launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g);
+    TRY(check_launch(h, "warp", 1));
+    TRY(run_derivatives(h, g, fr[0], h->c[C_WARPED]));
+    // solve (366-406)
+    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], false, p));
+    // u += du, v += dv, median (409-449); the finest level writes the caller's flow containers
+    {
+      const float* a[2] = {u, v};
+      const float* b[2] = {h->c[C_DU0], h->c[C_DV0]};
+      float* out[2] = {level == 0 ? out_u : u2, level == 0 ? out_v : v2};
+      launch_add_median(st, a, b, out, 2, g.w, g.h, g.pitch, median);
+      TRY(check_launch(h, "add_median", 1));
+      std::swap(u, u2); std::swap(v, v2);
+    }
+    pw = cw; ph = ch;
+    --level;
+    ++h->levels_run;
+  }
+  return FLOW2D_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* flow2d_version(void) { return "flow2d-b200 0.1.0 sm_100a"; }
+
+void flow2d_default_params(flow2d_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof *p);
+  p->warp_levels_count = 50;     // main.cpp:70
+  p->warp_scale_factor = 0.9f;   // main.cpp:71
+  p->outer_iterations_count = 40;
+  p->inner_iterations_count = 5;
+  p->equation_alpha = 35.0f;
+  p->equation_smoothness = 0.001f;
+  p->equation_data = 0.001f;
+  p->median_radius = 5;
+  p->gaussian_sigma = 1.5f;
+  p->sweeps_per_pass = 0;
+  p->resident_levels = 0;
+}
+
+size_t flow2d_max_warp_level(size_t width, size_t height, float scale_factor) {
+  // optical_flow_base_2d.cpp:36-59, same fp32 expressions
+  size_t r_width = 1, r_height = 1, level_counter = 1;
+  while (scale_factor < 1.f) {
+    const float scale = std::pow(scale_factor, static_cast<float>(level_counter));
+    r_width = static_cast<size_t>(std::ceil(width * scale));
+    r_height = static_cast<size_t>(std::ceil(height * scale));
+    if (r_width < 4 || r_height < 4) break;
+    ++level_counter;
+  }
+  if (r_width == 1 || r_height == 1) --level_counter;
+  return level_counter;
+}
+
+int flow2d_level_geometry(size_t width, size_t height, float scale_factor, int level, size_t* cw, size_t* ch, float* hx,
+                          float* hy) {
+  if (!cw || !ch || !hx || !hy || level < 0) return FLOW2D_ERR_INVALID_ARGUMENT;
+  // optical_flow_2d.cpp:268-272
+  const float scale = std::pow(scale_factor, static_cast<float>(level));
+  *cw = static_cast<size_t>(std::ceil(width * scale));
+  *ch = static_cast<size_t>(std::ceil(height * scale));
+  *hx = width / static_cast<float>(*cw);
+  *hy = height / static_cast<float>(*ch);
+  return FLOW2D_OK;
+}
+
+int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, int constancy) {
+  if (!out) return FLOW2D_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (width < 4 || height < 4 || width > 65536 || height > 65536) return FLOW2D_ERR_INVALID_ARGUMENT;
+  if (constancy != FLOW2D_GREY && constancy != FLOW2D_GRADIENT) return FLOW2D_ERR_UNSUPPORTED;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    (void)cudaGetLastError();
+    return FLOW2D_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return FLOW2D_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FLOW2D_ERR_CUDA;
+  if (prop.major != 10) return FLOW2D_ERR_NO_DEVICE;  // sm_100a only: no other code path exists
+
+  flow2d_handle* h = new (std::nothrow) flow2d_handle;
+  if (!h) return FLOW2D_ERR_OUT_OF_MEMORY;
+  h->device = device;
+  h->W = width; h->H = height;
+  h->pitch = (width + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
+  h->constancy = constancy;
+  const int ncont = constancy == FLOW2D_GRADIENT ? C_COUNT : C_J0;
+  const size_t csize = h->pitch * height;
+  if (cudaMalloc(&h->pool, csize * ncont * sizeof(float)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete h;
+    return FLOW2D_ERR_OUT_OF_MEMORY;
+  }
+  for (int i = 0; i < ncont; i++) h->c[i] = h->pool + csize * i;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
+      solve_pass_configure() != cudaSuccess || cudaMemsetAsync(h->pool, 0, csize * ncont * sizeof(float), h->own_stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    flow2d_destroy(h);
+    return FLOW2D_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  *out = h;
+  return FLOW2D_OK;
+}
+
+int flow2d_destroy(flow2d_handle* h) {
+  if (!h) return FLOW2D_OK;
+  cudaSetDevice(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->pool) cudaFree(h->pool);
+  delete h;
+  return FLOW2D_OK;
+}
+
+const char* flow2d_last_error(const flow2d_handle* h) { return h ? h->err.c_str() : "null handle"; }
+size_t flow2d_pitch_elems(const flow2d_handle* h) { return h ? h->pitch : 0; }
+size_t flow2d_width(const flow2d_handle* h) { return h ? h->W : 0; }
+size_t flow2d_height(const flow2d_handle* h) { return h ? h->H : 0; }
+
+int flow2d_set_stream(flow2d_handle* h, void* cuda_stream) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return FLOW2D_OK;
+}
+void* flow2d_get_stream(const flow2d_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launches, int* levels_run, float* device_ms) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  if (kernel_launches) *kernel_launches = h->launches;
+  if (levels_run) *levels_run = h->levels_run;
+  if (device_ms) *device_ms = h->device_ms;
+  return FLOW2D_OK;
+}
+
+int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, float* d_flow_u,
+                          float* d_flow_v, const flow2d_params* p) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null image pointer");
+  if (!aligned16(d_frame_0) || !aligned16(d_frame_1) || !aligned16(d_flow_u) || !aligned16(d_flow_v))
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "device containers must be 16-byte aligned");
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->launches = 0;
+  return compute_on_device(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p);
+}
+
+int flow2d_compute(flow2d_handle* h, const float* frame_0, const float* frame_1, float* flow_u, float* flow_v,
+                   const flow2d_params* p) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  if (!frame_0 || !frame_1 || !flow_u || !flow_v) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null image pointer");
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->launches = 0;
+  const size_t row = h->W * sizeof(float), dpitch = h->pitch * sizeof(float);
+  cudaStream_t st = h->stream;
+  CU_TRY(h, cudaEventRecord(h->ev_start, st));
+  // CopyData2DtoDevice (cuda_utils.cpp:66-84)
+  CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN0], dpitch, frame_0, row, row, h->H, cudaMemcpyHostToDevice, st));
+  CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN1], dpitch, frame_1, row, row, h->H, cudaMemcpyHostToDevice, st));
+  float* out_u = h->c[C_OUT_U];
+  float* out_v = h->c[C_OUT_V];
+  int rc = compute_on_device(h, h->c[C_IN0], h->c[C_IN1], out_u, out_v, p);
+  if (rc != FLOW2D_OK) {
+    cudaStreamSynchronize(st);
+    return rc;
+  }
+  // CopyData2DFromDevice (cuda_utils.cpp:87-105)
+  CU_TRY(h, cudaMemcpy2DAsync(flow_u, row, out_u, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaMemcpy2DAsync(flow_v, row, out_v, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));
+  CU_TRY(h, cudaEventRecord(h->ev_stop, st));
+  CU_TRY(h, cudaStreamSynchronize(st));
+  CU_TRY(h, cudaEventElapsedTime(&h->device_ms, h->ev_start, h->ev_stop));
+  return FLOW2D_OK;
+}
+
+// ---- per-stage API ----
+#define STAGE_PROLOGUE(h)                                    \
+  if (!(h)) return FLOW2D_ERR_INVALID_ARGUMENT;              \
+  CU_TRY((h), cudaSetDevice((h)->device))
+
+int flow2d_stage_blur(flow2d_handle* h, const float* d_in, float* d_out, size_t w, size_t hh, float sigma) {
+  STAGE_PROLOGUE(h);
+  if (!d_in || !d_out || d_in == d_out) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "blur: bad buffers (in-place is refused)");
+  TRY(check_level(h, w, hh));
+  GaussTaps taps;
+  TRY(gauss_taps(h, sigma, &taps));
+  launch_blur(h->stream, d_in, d_out, (int)w, (int)hh, (int)h->pitch, taps);
+  return check_launch(h, "blur", 1);
+}
+
+int flow2d_stage_resample(flow2d_handle* h, const float* d_in, size_t iw, size_t ih, float* d_out, size_t ow, size_t oh) {
+  STAGE_PROLOGUE(h);
+  if (!d_in || !d_out || d_in == d_out) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "resample: bad buffers (in-place is refused)");
+  if (iw < 1 || ih < 1 || ow < 1 || oh < 1 || iw > h->W || ow > h->W || ih > h->H || oh > h->H)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "resample: size outside the container");
+  const float* in[2] = {d_in, d_in};
+  float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP0]};
+  float* out[2] = {d_out, d_out};
+  launch_resample(h->stream, in, tmp, out, 1, (int)iw, (int)ih, (int)ow, (int)oh, (int)h->pitch);
+  return check_launch(h, "resample", 2);
+}
+
+int flow2d_stage_warp(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, const float* d_flow_u,
+                      const float* d_flow_v, float* d_out, size_t w, size_t hh, float hx, float hy) {
+  STAGE_PROLOGUE(h);
+  if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v || !d_out || d_out == d_frame_1 || d_out == d_frame_0)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "warp: bad buffers (in-place is refused)");
+  TRY(check_level(h, w, hh));
+  launch_warp(h->stream, d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_out, geom(h, w, hh, hx, hy));
+  return check_launch(h, "warp", 1);
+}
+
+int flow2d_stage_solve(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, const float* d_flow_u,
+                       const float* d_flow_v, float* d_flow_du, float* d_flow_dv, float* d_phi, float* d_ksi, size_t w,
+                       size_t hh, float hx, float hy, const flow2d_params* p) {
+  STAGE_PROLOGUE(h);
+  if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v || !d_flow_du || !d_flow_dv || !p)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "solve: null buffer");
+  if ((d_phi == nullptr) != (d_ksi == nullptr)) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "solve: phi and ksi go together");
+  const void* ptrs[] = {d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, d_phi, d_ksi};
+  for (const void* q : ptrs)
+    if (!aligned16(q)) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "solve: containers must be 16-byte aligned");
+  if (p->sweeps_per_pass < 0 || p->sweeps_per_pass > FLOW2D_MAX_SWEEPS_PER_PASS)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "sweeps_per_pass must be 0..%d", FLOW2D_MAX_SWEEPS_PER_PASS);
+  TRY(check_level(h, w, hh));
+  const LevelGeom g = geom(h, w, hh, hx, hy);
+  TRY(run_derivatives(h, g, d_frame_0, d_frame_1));
+  const bool want_phi = d_phi != nullptr;
+  return run_solve(h, g, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1],
+                   want_phi ? d_phi : h->c[C_PHI], want_phi ? d_ksi : h->c[C_KSI], want_phi, p);
+}
+
+int flow2d_stage_add(flow2d_handle* h, float* d_a, const float* d_b, size_t w, size_t hh) {
+  STAGE_PROLOGUE(h);
+  if (!d_a || !d_b) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "add: null buffer");
+  TRY(check_level(h, w, hh));
+  launch_add(h->stream, d_a, d_b, (int)w, (int)hh, (int)h->pitch);
+  return check_launch(h, "add", 1);
+}
+
+int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b, float* d_out, size_t w, size_t hh,
+                            size_t radius) {
+  STAGE_PROLOGUE(h);
+  if (!d_a || !d_out || d_a == d_out || d_b == d_out)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "median: bad buffers (in-place is refused)");
+  TRY(check_level(h, w, hh));
+  int r = 1;
+  TRY(normalise_median(h, radius, &r));
+  const float* a[2] = {d_a, d_a};
+  const float* b[2] = {d_b, d_b};
+  float* out[2] = {d_out, d_out};
+  launch_add_median(h->stream, a, d_b ? b : nullptr, out, 1, (int)w, (int)hh, (int)h->pitch, r);
+  return check_launch(h, "add_median", 1);
+}
+
+int flow2d_stage_median(flow2d_handle* h, const float* d_in, float* d_out, size_t w, size_t hh, size_t radius) {
+  return flow2d_stage_add_median(h, d_in, nullptr, d_out, w, hh, radius);
+}
+
+}  // extern "C"

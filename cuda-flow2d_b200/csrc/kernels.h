@@ -1,0 +1,47 @@
+// kernels.h -- launch interface of the sm_100a kernels (internal; the public boundary is include/flow2d.h).
+#pragma once
+
+#include "common.cuh"
+
+namespace flow2d {
+
+// ---- pyramid.cu ----
+void launch_blur(cudaStream_t st, const float* in, float* out, int w, int h, int pitch, const GaussTaps& taps);
+void launch_resample(cudaStream_t st, const float* const* in, float* const* tmp, float* const* out, int count,
+                     int iw, int ih, int ow, int oh, int pitch);
+void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float* u, const float* v, float* out,
+                 const LevelGeom& g);
+void launch_derivatives(cudaStream_t st, const float* f0, const float* f1w, float* fx, float* fy, float* ft,
+                        const LevelGeom& g);
+void launch_grad_tensor(cudaStream_t st, const float* fx, const float* fy, const float* ft, float* const* J,
+                        const LevelGeom& g);
+
+// ---- median.cu ----
+void launch_add_median(cudaStream_t st, const float* const* a, const float* const* b, float* const* out, int count,
+                       int w, int h, int pitch, int radius);
+void launch_add(cudaStream_t st, float* a, const float* b, int w, int h, int pitch);
+
+// ---- solve.cu ----
+constexpr int kSolveLW = 64, kSolveLH = 64;  // shared-memory region of one CTA (output tile + halo)
+
+struct SolveArgs {
+  const float *fx, *fy, *ft;      // brightness derivatives of the level (launch_derivatives)
+  const float* J[5];              // gradient-constancy tensor J11 J22 J12 J13 J23 (gradient mode only)
+  const float *u, *v;             // flow of the level (constant during the solve)
+  const float *du_in, *dv_in;     // current increment; null = all zero (first pass of a level)
+  const float *phi_in, *ksi_in;   // null = compute the robust weights in this pass from du_in/dv_in
+  float *du_out, *dv_out;
+  float *phi_out, *ksi_out;       // null = do not store the robust weights
+  int w, h, pitch;
+  float hx, hy, alpha, e_smooth, e_data;
+  int sweeps;                     // Jacobi sweeps in this pass
+  int outer;                      // 1, or (resident mode, grid 1x1) the number of outer iterations
+  int ow, oh;                     // output tile of one CTA (ow % 4 == 0)
+  int halo_x, halo_y;             // region origin = tile origin - halo; halo_x % 4 == 0
+};
+
+size_t solve_pass_smem_bytes();
+cudaError_t solve_pass_configure();
+void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y);
+
+}  // namespace flow2d

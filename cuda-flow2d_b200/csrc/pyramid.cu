@@ -1,0 +1,234 @@
+// pyramid.cu -- presmoothing, area resampling (restriction + prolongation), backward warping and
+// derivative / motion-tensor assembly.  sm_100a, compiled with -fmad=false (see common.cuh).
+//
+// Replaces, with identical results:
+//   convolutionRowsKernel + convolutionColumnsKernel  src/kernels/convolution_2d.cu:74-261
+//   resample_x + resample_y                           src/kernels/resample_2d.cu:34-118
+//   registration_2d                                   src/kernels/registration_2d.cu:34-74
+//   the fx/fy/ft (+ gradient-constancy tensor) part of solve_2d / solve_2d_grad
+//                                                     src/kernels/solve_2d.cu:311-329, 798-884
+#include "kernels.h"
+
+namespace flow2d {
+
+// ---------------------------------------------------------------------------------------------
+// Gaussian presmoothing: one fused kernel (rows pass into shared memory, then columns pass).
+// Zero padding in both directions, ascending-j fma chain from sum = 0 (convolution_2d.cu:150-166).
+// Algorithmic traffic: 1 read + 1 write per pixel (the reference's two kernels: 2R + 2W).
+// ---------------------------------------------------------------------------------------------
+constexpr int kBlurTW = 64;  // output tile width  (threads in x)
+constexpr int kBlurTH = 32;  // output tile height (each of the 8 thread rows produces 4 outputs)
+
+__global__ void __launch_bounds__(512)
+blur_kernel(const float* __restrict__ in, float* __restrict__ out, int w, int h, int pitch, GaussTaps taps) {
+  extern __shared__ float smem[];
+  const int r = taps.radius;
+  const int IW = kBlurTW + 2 * r;        // staged input width
+  const int IH = kBlurTH + 2 * r;        // staged input / row-pass height
+  float* s_in = smem;                    // IH x IW   input tile, zero outside the image
+  float* s_row = smem + IH * IW;         // IH x TW   row-pass result, zero for rows outside the image
+  const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+
+  for (int i = tid; i < IH * IW; i += nthreads) {
+    int ly = i / IW, lx = i - ly * IW;
+    int gx = x0 - r + lx, gy = y0 - r + ly;
+    s_in[i] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? in[(size_t)gy * pitch + gx] : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < IH * kBlurTW; i += nthreads) {
+    int ly = i / kBlurTW, lx = i - ly * kBlurTW;
+    int gy = y0 - r + ly;
+    float sum = 0.f;
+    if (gy >= 0 && gy < h) {
+      const float* row = s_in + ly * IW + lx + r;
+      for (int j = -r; j <= r; j++) sum = fmaf(taps.c[r - j], row[j], sum);
+    }
+    s_row[i] = sum;
+  }
+  __syncthreads();
+  for (int i = tid; i < kBlurTH * kBlurTW; i += nthreads) {
+    int ly = i / kBlurTW, lx = i - ly * kBlurTW;
+    int gx = x0 + lx, gy = y0 + ly;
+    if (gx < w && gy < h) {
+      const float* col = s_row + (ly + r) * kBlurTW + lx;
+      float sum = 0.f;
+      for (int j = -r; j <= r; j++) sum = fmaf(taps.c[r - j], col[j * kBlurTW], sum);
+      out[(size_t)gy * pitch + gx] = sum;
+    }
+  }
+}
+
+void launch_blur(cudaStream_t st, const float* in, float* out, int w, int h, int pitch, const GaussTaps& taps) {
+  const int r = taps.radius;
+  size_t smem = sizeof(float) * ((kBlurTH + 2 * r) * (kBlurTW + 2 * r) + (kBlurTH + 2 * r) * kBlurTW);
+  dim3 grid((w + kBlurTW - 1) / kBlurTW, (h + kBlurTH - 1) / kBlurTH), block(64, 8);
+  blur_kernel<<<grid, block, smem, st>>>(in, out, w, h, pitch, taps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Area resampling, one axis per kernel, two images per launch (blockIdx.z).
+// The index path is the reference's fp32 arithmetic verbatim (resample_2d.cu:44-51):
+//   delta = in/(float)out (div.rn), left_f = x*delta, right_f = (x+1)*delta (plain mul),
+//   left_i = floor, right_i = min(in, ceil); accumulation value = fma(frac, in[..], value).
+// ---------------------------------------------------------------------------------------------
+struct ResamplePair {
+  const float* in[2];
+  float* out[2];
+};
+
+template <bool ALONG_X>
+__global__ void __launch_bounds__(256)
+resample_kernel(ResamplePair io, int out_w, int out_h, int in_n, int out_n, int pitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= out_w || y >= out_h) return;
+  const float* __restrict__ in = blockIdx.z ? io.in[1] : io.in[0];
+  float* __restrict__ out = blockIdx.z ? io.out[1] : io.out[0];
+  const int o = ALONG_X ? x : y;
+  const float delta = (float)in_n / (float)out_n;
+  const float normalization = (float)out_n / (float)in_n;
+  const float left_f = (float)o * delta;
+  const float right_f = (float)(o + 1) * delta;
+  const int left_i = (int)floorf(left_f);
+  const int right_i = min(in_n, (int)ceilf(right_f));
+  const int n = right_i - left_i;
+  const float* src = ALONG_X ? in + (size_t)y * pitch + left_i : in + (size_t)left_i * pitch + x;
+  const size_t stride = ALONG_X ? 1 : (size_t)pitch;
+  float value = 0.f;
+  for (int j = 0; j < n; j++) {
+    float frac = 1.f;
+    if (j == 0) frac = (float)(left_i + 1) - left_f;
+    if (j == n - 1) frac = right_f - (float)(left_i + j);
+    if (n == 1) frac = delta;
+    value = fmaf(frac, src[j * stride], value);
+  }
+  out[(size_t)y * pitch + x] = value * normalization;
+}
+
+// (iw x ih) -> (ow x oh) for `count` (1 or 2) images; tmp[] are scratch containers.
+void launch_resample(cudaStream_t st, const float* const* in, float* const* tmp, float* const* out, int count,
+                     int iw, int ih, int ow, int oh, int pitch) {
+  ResamplePair px, py;
+  for (int i = 0; i < 2; i++) {
+    int k = i < count ? i : 0;
+    px.in[i] = in[k]; px.out[i] = tmp[k];
+    py.in[i] = tmp[k]; py.out[i] = out[k];
+  }
+  dim3 block(32, 8);
+  dim3 gx((ow + 31) / 32, (ih + 7) / 8, count);
+  resample_kernel<true><<<gx, block, 0, st>>>(px, ow, ih, iw, ow, pitch);
+  dim3 gy((ow + 31) / 32, (oh + 7) / 8, count);
+  resample_kernel<false><<<gy, block, 0, st>>>(py, ow, oh, ih, oh, pitch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward bilinear registration of frame 1 by the current flow (registration_2d.cu:48-72).
+// As compiled upstream: x_f = fma(rcp.rn(hx), u, (float)x); bounds (float)(w-1); the blend is
+// fma(w11,f11, fma(w01,f01, fma(f00,w00, w10*f10))).  Index work (floor, clamp, OOB/NaN test)
+// is bit exact by construction.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+warp_kernel(const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ u,
+            const float* __restrict__ v, float* __restrict__ out, int w, int h, int pitch, float rhx, float rhy) {
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (xx >= w || yy >= h) return;
+  const size_t c = (size_t)yy * pitch + xx;
+  const float x_f = fmaf(rhx, u[c], (float)xx);
+  const float y_f = fmaf(rhy, v[c], (float)yy);
+  const float bx = (float)(w - 1), by = (float)(h - 1);
+  float val;
+  if ((x_f < 0.f) || (x_f > bx) || (y_f < 0.f) || (y_f > by) || isnan(x_f) || isnan(y_f)) {
+    val = f0[c];
+  } else {
+    const int x = (int)floorf(x_f), y = (int)floorf(y_f);
+    const float dx = x_f - (float)x, dy = y_f - (float)y;
+    const int x1 = min(w - 1, x + 1), y1 = min(h - 1, y + 1);
+    const float ox = 1.f - dx, oy = 1.f - dy;
+    const float w00 = ox * oy, w10 = dx * oy, w01 = ox * dy, w11 = dx * dy;
+    const float* r0 = f1 + (size_t)y * pitch;
+    const float* r1 = f1 + (size_t)y1 * pitch;
+    val = w10 * r0[x1];
+    val = fmaf(r0[x], w00, val);
+    val = fmaf(w01, r1[x], val);
+    val = fmaf(w11, r1[x1], val);
+  }
+  out[c] = val;
+}
+
+void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float* u, const float* v, float* out,
+                 const LevelGeom& g) {
+  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
+  warp_kernel<<<grid, block, 0, st>>>(f0, f1, u, v, out, g.w, g.h, g.pitch, 1.f / g.hx, 1.f / g.hy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Derivative assembly.  fx, fy, ft depend only on frame 0 and the warped frame 1, i.e. they are
+// constant for a whole pyramid level, while the reference recomputes them in every one of the
+// outer*(1+inner) kernel launches of the level (solve_2d.cu:164-174, 311-321).  They are computed
+// here once per level with the reference's expression tree:
+//   fx = (((f0[x+1]-f0[x-1]) + f1[x+1]) - f1[x-1]) / (4*hx)   (mirrored neighbours, div.rn)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+derivatives_kernel(const float* __restrict__ f0, const float* __restrict__ f1, float* __restrict__ fx,
+                   float* __restrict__ fy, float* __restrict__ ft, int w, int h, int pitch, float hx4, float hy4) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int xm = mirror_clamp(x - 1, w), xp = mirror_clamp(x + 1, w);
+  const int ym = mirror_clamp(y - 1, h), yp = mirror_clamp(y + 1, h);
+  const size_t row = (size_t)y * pitch;
+  const size_t c = row + x;
+  fx[c] = (((f0[row + xp] - f0[row + xm]) + f1[row + xp]) - f1[row + xm]) / hx4;
+  fy[c] = (((f0[(size_t)yp * pitch + x] - f0[(size_t)ym * pitch + x]) + f1[(size_t)yp * pitch + x]) -
+           f1[(size_t)ym * pitch + x]) / hy4;
+  ft[c] = f1[c] - f0[c];
+}
+
+// Gradient-constancy motion tensor (solve_2d.cu:868-884) from the fx/fy/ft planes.  The reference
+// takes the central differences inside a 16x8 CUDA block whose 1-px halo of fx/fy/ft is the
+// block-edge thread's OWN value (solve_2d.cu:813-841), so its result depends on that tiling; it is
+// reproduced here (tx = x%16, ty = y%8).  The cell just outside the image in a partial block is
+// uninitialised shared memory upstream; here it is defined as the own value.
+// hx_1 = (float)(1.0/(2.0*hx)) is computed in double upstream and passed in.
+__global__ void __launch_bounds__(256)
+grad_tensor_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ ft,
+                   float* __restrict__ J11, float* __restrict__ J22, float* __restrict__ J12,
+                   float* __restrict__ J13, float* __restrict__ J23, int w, int h, int pitch, float hx_1, float hy_1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int tx = x & 15, ty = y & 7;
+  const int xl = (tx == 0) ? x : x - 1;
+  const int xr = (tx == 15 || x + 1 >= w) ? x : x + 1;
+  const int yu = (ty == 0) ? y : y - 1;
+  const int yb = (ty == 7 || y + 1 >= h) ? y : y + 1;
+  const size_t row = (size_t)y * pitch, up = (size_t)yu * pitch, dn = (size_t)yb * pitch;
+  const float fxx = (fx[row + xr] - fx[row + xl]) * hx_1;
+  const float fxy = (fx[dn + x] - fx[up + x]) * hy_1;
+  const float fyy = (fy[dn + x] - fy[up + x]) * hy_1;
+  const float fxt = (ft[row + xr] - ft[row + xl]) * hx_1;
+  const float fyt = (ft[dn + x] - ft[up + x]) * hy_1;
+  const size_t c = row + x;
+  J11[c] = fmaf(fxx, fxx, fxy * fxy);
+  J22[c] = fmaf(fxy, fxy, fyy * fyy);
+  J12[c] = fmaf(fxx, fxy, fxy * fyy);
+  J13[c] = fmaf(fxx, fxt, fxy * fyt);
+  J23[c] = fmaf(fxy, fxt, fyy * fyt);
+}
+
+void launch_derivatives(cudaStream_t st, const float* f0, const float* f1w, float* fx, float* fy, float* ft,
+                        const LevelGeom& g) {
+  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
+  derivatives_kernel<<<grid, block, 0, st>>>(f0, f1w, fx, fy, ft, g.w, g.h, g.pitch, g.hx * 4.f, g.hy * 4.f);
+}
+
+void launch_grad_tensor(cudaStream_t st, const float* fx, const float* fy, const float* ft, float* const* J,
+                        const LevelGeom& g) {
+  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
+  const float hx_1 = (float)(1.0 / (2.0 * (double)g.hx)), hy_1 = (float)(1.0 / (2.0 * (double)g.hy));
+  grad_tensor_kernel<<<grid, block, 0, st>>>(fx, fy, ft, J[0], J[1], J[2], J[3], J[4], g.w, g.h, g.pitch, hx_1, hy_1);
+}
+
+}  // namespace flow2d

@@ -1,0 +1,154 @@
+/*
+ * flow2d.h -- C ABI of the B200-native 2D variational optical-flow solver.
+ *
+ * This is the drop-in boundary for the hot path of axruff/cuda-flow2d
+ * (OpticalFlow2D::ComputeFlow and the six CudaOperation*2D operators under it).  Plain pointers
+ * and sizes only; no C++ or torch types.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *   - All images are fp32, row-major.  HOST images are dense (row stride = width).  DEVICE images
+ *     are "containers": the handle's pitch (flow2d_pitch_elems) floats per row, height rows;
+ *     a pyramid level of size cw x ch occupies the top-left corner of a container, exactly like
+ *     the reference's pitched containers (src/optical_flow/optical_flow_2d.cpp:84-140).
+ *   - Every function returns FLOW2D_OK (0) or a negative flow2d_status; nothing throws or aborts.
+ *     flow2d_last_error() gives the message of the last failure on that handle.
+ *   - One handle = one device + one stream.  Handles are independent (one per GPU / host thread);
+ *     a single handle is not thread-safe (same as the reference class).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef FLOW2D_H_
+#define FLOW2D_H_
+
+#include <stddef.h>
+
+#if defined(__GNUC__)
+#define FLOW2D_API __attribute__((visibility("default")))
+#else
+#define FLOW2D_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flow2d_handle flow2d_handle;
+
+typedef enum flow2d_status {
+  FLOW2D_OK = 0,
+  FLOW2D_ERR_INVALID_ARGUMENT = -1, /* bad size / pointer / parameter (reference: printf + early return) */
+  FLOW2D_ERR_CUDA = -2,             /* a CUDA runtime call failed (reference: CheckCudaError, cuda_utils.h:33) */
+  FLOW2D_ERR_NO_DEVICE = -3,        /* no usable CUDA device (reference: main.cpp exit code 1) */
+  FLOW2D_ERR_OUT_OF_MEMORY = -4,    /* container allocation failed (optical_flow_2d.cpp:112-137) */
+  FLOW2D_ERR_UNSUPPORTED = -5       /* parameter outside what the path supports (e.g. median size 9) */
+} flow2d_status;
+
+/* src/data_types/data_structs.h:27 `enum class DataConstancy` */
+typedef enum flow2d_constancy {
+  FLOW2D_GREY = 0,     /* brightness constancy (the only value reachable from the reference CLI) */
+  FLOW2D_GRADIENT = 1  /* gradient constancy, reproducing solve_2d_grad incl. its 16x8 tile artefact */
+} flow2d_constancy;
+
+/* The nine solver parameters of OpticalFlow2D::ComputeFlow, passed there by name through
+ * OperationParameters (src/optical_flow/optical_flow_2d.cpp:160-168, src/main.cpp:192-201),
+ * plus scheduling knobs that never change results. */
+typedef struct flow2d_params {
+  size_t warp_levels_count;      /* "warp_levels_count"      settings.xml Warping@levels      */
+  float  warp_scale_factor;      /* "warp_scale_factor"      settings.xml Warping@scaling     */
+  size_t outer_iterations_count; /* "outer_iterations_count" settings.xml Iterations@outer    */
+  size_t inner_iterations_count; /* "inner_iterations_count" settings.xml Iterations@inner    */
+  float  equation_alpha;         /* "equation_alpha"         settings.xml Model@alpha         */
+  float  equation_smoothness;    /* "equation_smoothness"    settings.xml Model@e_smooth      */
+  float  equation_data;          /* "equation_data"          settings.xml Model@e_data        */
+  size_t median_radius;          /* "median_radius" (window diameter: 1 = off, 3, 5, 7; even values -1) */
+  float  gaussian_sigma;         /* "gaussian_sigma"         settings.xml Model@sigma; <= 0 = off */
+  /* scheduling (0 = automatic); results are identical for every value */
+  int    sweeps_per_pass;        /* Jacobi sweeps fused into one solve_pass launch (1..FLOW2D_MAX_SWEEPS_PER_PASS) */
+  int    resident_levels;        /* 0 auto / 1 = run small levels in a single resident CTA / -1 = never */
+} flow2d_params;
+
+#define FLOW2D_MAX_SWEEPS_PER_PASS 7
+
+/* Fills *p with the reference's argv-form defaults (src/main.cpp:70-80). */
+FLOW2D_API void flow2d_default_params(flow2d_params* p);
+
+/* ---- lifetime: replaces OpticalFlow2D::Initialize / Destroy ------------------------------------
+ * (src/optical_flow/optical_flow_2d.cpp:48-140, 571-590).  Allocates every device container,
+ * stream and event for images of exactly width x height on CUDA device `device`. */
+FLOW2D_API int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, int constancy);
+FLOW2D_API int flow2d_destroy(flow2d_handle* h);
+FLOW2D_API const char* flow2d_last_error(const flow2d_handle* h);
+
+/* container geometry (reference: DataSize3.pitch / sizeof(float), cuMemAllocPitch) */
+FLOW2D_API size_t flow2d_pitch_elems(const flow2d_handle* h);
+FLOW2D_API size_t flow2d_width(const flow2d_handle* h);
+FLOW2D_API size_t flow2d_height(const flow2d_handle* h);
+/* The handle launches everything on this stream (a cudaStream_t).  NULL = handle-owned stream. */
+FLOW2D_API int flow2d_set_stream(flow2d_handle* h, void* cuda_stream);
+FLOW2D_API void* flow2d_get_stream(const flow2d_handle* h);
+
+/* ---- the hot path: replaces OpticalFlow2D::ComputeFlow ------------------------------------------
+ * (src/optical_flow/optical_flow_2d.cpp:142-569).
+ * flow2d_compute: host in, host out (dense width*height floats each); blocks until u, v are
+ * written, like the reference (H2D, solve, D2H).
+ * flow2d_compute_device: frames and flow stay on the device as containers (pitch =
+ * flow2d_pitch_elems); asynchronous on the handle's stream. */
+FLOW2D_API int flow2d_compute(flow2d_handle* h, const float* frame_0, const float* frame_1,
+                   float* flow_u, float* flow_v, const flow2d_params* p);
+FLOW2D_API int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
+                          float* d_flow_u, float* d_flow_v, const flow2d_params* p);
+
+/* Diagnostics of the last flow2d_compute*(): kernels launched, pyramid levels run, and (after
+ * flow2d_compute only) the device time in ms between the first H2D and the last D2H -- the span
+ * of the reference's "Total GPU computation time" (optical_flow_2d.cpp:179,548-554). */
+FLOW2D_API int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launches, int* levels_run, float* device_ms);
+
+/* ---- level table: replaces OpticalFlowBase2D::GetMaxWarpLevel and the per-level size formulas ---
+ * (src/optical_flow/optical_flow_base_2d.cpp:36-59, src/optical_flow/optical_flow_2d.cpp:268-272).
+ * Host-only integer/fp32 arithmetic, bit-exact with the reference. */
+FLOW2D_API size_t flow2d_max_warp_level(size_t width, size_t height, float scale_factor);
+FLOW2D_API int flow2d_level_geometry(size_t width, size_t height, float scale_factor, int level,
+                          size_t* cw, size_t* ch, float* hx, float* hy);
+
+/* ---- per-stage API on device containers -----------------------------------------------------------
+ * One call per reference operator, so each kernel can be checked against the reference's on the same
+ * buffers.  All pointers are device containers of this handle's geometry.  Asynchronous on the
+ * handle's stream.  In-place use (input == output) is refused like in the reference, except for
+ * flow2d_stage_add. */
+
+/* CudaOperationConvolution2D::Execute (cuda_operation_convolution_2d.cpp:132-176): zero-padded
+ * separable Gaussian, radius = (size_t)(3*sigma) <= 16. */
+FLOW2D_API int flow2d_stage_blur(flow2d_handle* h, const float* d_in, float* d_out, size_t w, size_t h_, float sigma);
+/* CudaOperationResample2D::Execute (cuda_operation_resample_2d.cpp:76-106): area resampling
+ * (iw x ih) -> (ow x oh), x pass then y pass. */
+FLOW2D_API int flow2d_stage_resample(flow2d_handle* h, const float* d_in, size_t iw, size_t ih,
+                          float* d_out, size_t ow, size_t oh);
+/* CudaOperationRegistration2D::Execute (cuda_operation_registration_2d.cpp:74-128). */
+FLOW2D_API int flow2d_stage_warp(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
+                      const float* d_flow_u, const float* d_flow_v, float* d_out,
+                      size_t w, size_t h_, float hx, float hy);
+/* CudaOperationSolve2D::Execute (cuda_operation_solve_2d.cpp:106-315): zero du/dv, then
+ * outer x (phi/ksi + inner x Jacobi sweep).  d_frame_1 is the WARPED second frame.  Results in
+ * d_flow_du, d_flow_dv; d_phi / d_ksi (optional, may be NULL) receive the last outer iteration's
+ * robust weights.  Uses p->outer/inner/alpha/smoothness/data and the scheduling knobs. */
+FLOW2D_API int flow2d_stage_solve(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
+                       const float* d_flow_u, const float* d_flow_v,
+                       float* d_flow_du, float* d_flow_dv, float* d_phi, float* d_ksi,
+                       size_t w, size_t h_, float hx, float hy, const flow2d_params* p);
+/* CudaOperationAdd2D::Execute (cuda_operation_add_2d.cpp:75-106): d_a += d_b. */
+FLOW2D_API int flow2d_stage_add(flow2d_handle* h, float* d_a, const float* d_b, size_t w, size_t h_);
+/* CudaOperationMedian2D::Execute (cuda_operation_median_2d.cpp:77-155): radius 1 = copy, even
+ * values are decremented, 3/5/7 filter with mirrored borders; anything else is
+ * FLOW2D_ERR_UNSUPPORTED (the reference prints an error and leaves d_out untouched). */
+FLOW2D_API int flow2d_stage_median(flow2d_handle* h, const float* d_in, float* d_out, size_t w, size_t h_, size_t radius);
+/* Fused 2 x add + 2 x median of one level (optical_flow_2d.cpp:409-449): out = median(a + b). */
+FLOW2D_API int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b, float* d_out,
+                            size_t w, size_t h_, size_t radius);
+
+/* Library identification: "flow2d-b200 <version> sm_100a". */
+FLOW2D_API const char* flow2d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOW2D_H_ */
