@@ -316,6 +316,19 @@ extern "C" {
 
 const char* flow2d_version(void) { return "flow2d-b200 0.1.0 sm_100a"; }
 
+void* flow2d_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void flow2d_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 void flow2d_default_params(flow2d_params* p) {
   if (!p) return;
   std::memset(p, 0, sizeof *p);

@@ -1,0 +1,139 @@
+// main.cpp -- the cuda-flow2d command line, same three argv forms, output files and exit codes as
+// the reference (src/main.cpp:46-229):
+//   cuda-flow2d                      settings.xml in the current directory
+//   cuda-flow2d <settings file>
+//   cuda-flow2d <file1> <file2> <width> <height> [<counter>] <output path> [<alpha> <sigma>]
+// Outputs: <out><counter>flow-u-W-H.raw, flow-v-W-H.raw (float32), amp-W-H.raw (float32 magnitude).
+// Exit codes: 0 ok / usage, 1 no CUDA device, 2 input files unreadable, 3 settings unreadable.
+// Differences: no getchar() at exit; the 8-bit reader is wired to Mode@imageType="8-bit";
+// files are also looked up under Input/Path@inputPath when they are not found in the CWD.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "flow2d.h"
+#include "optical_flow_2d.h"
+#include "settings.h"
+
+using std::string;
+
+static bool exists(const string& p) {
+  std::FILE* f = std::fopen(p.c_str(), "rb");
+  if (f) std::fclose(f);
+  return f != nullptr;
+}
+
+int main(int argc, char** argv) {
+  std::printf("//----------------------------------------------------------------------//\n");
+  std::printf("//   2D optical flow, Blackwell-native (%s)   //\n", flow2d_version());
+  std::printf("//----------------------------------------------------------------------//\n");
+
+  size_t width = 584, height = 388;
+  size_t warp_levels_count = 50;  // src/main.cpp:70-80
+  float warp_scale_factor = 0.9f;
+  size_t outer_iterations_count = 40;
+  size_t inner_iterations_count = 5;
+  float equation_alpha = 35.0f;
+  float equation_smoothness = 0.001f;
+  float equation_data = 0.001f;
+  size_t median_radius = 5;
+  float gaussian_sigma = 1.5f;
+  DataConstancy data_constancy = DataConstancy::Grey;
+  string file_name1 = "rub1.raw", file_name2 = "rub2.raw";
+  string input_path = "./data/", output_path = "./data/output/", counter = "";
+  bool eight_bit = false;
+
+  if (argc == 6 || argc == 7 || argc == 9) {
+    file_name1 = argv[1];
+    file_name2 = argv[2];
+    width = std::atoi(argv[3]);
+    height = std::atoi(argv[4]);
+    // upstream reads argv[6] for every form (NULL for argc == 6); the 6-argument form means
+    // <file1> <file2> <W> <H> <output path> here
+    output_path = string(argc == 6 ? argv[5] : argv[6]);
+    if (argc == 7) counter = argv[5];
+    if (argc == 9) {
+      equation_alpha = std::atof(argv[7]);
+      gaussian_sigma = std::atof(argv[8]);
+      counter = "alpha" + string(argv[7]) + "_sigma" + string(argv[8]) + "_";
+    }
+  } else if (argc < 3) {
+    const string settingsFile = (argc == 1) ? "settings.xml" : string(argv[1]);
+    std::cout << "Reading settings: " << settingsFile << std::endl;
+    OpticFlow::Settings settings;
+    if (settings.LoadSettings(settingsFile) != 0) {
+      std::cout << settings.error << std::endl;
+      std::cout << "TERMINATING. Error reading settings: " << settingsFile << std::endl;
+      return 3;
+    }
+    std::cout << "OK" << std::endl << std::endl;
+    width = settings.width;
+    height = settings.height;
+    input_path = settings.inputPath;
+    output_path = settings.outputPath;
+    file_name1 = settings.fileName1;
+    file_name2 = settings.fileName2;
+    warp_levels_count = settings.levels;
+    warp_scale_factor = settings.warpScale;
+    outer_iterations_count = settings.iterOuter;
+    inner_iterations_count = settings.iterInner;
+    equation_alpha = settings.alpha;
+    equation_data = settings.e_data;
+    equation_smoothness = settings.e_smooth;
+    median_radius = settings.medianRadius;
+    gaussian_sigma = settings.sigma;
+    eight_bit = settings.imageType == "8-bit";
+    if (settings.constancy == "gradient") data_constancy = DataConstancy::Gradient;
+    if (!exists(file_name1) && exists(input_path + file_name1)) file_name1 = input_path + file_name1;
+    if (!exists(file_name2) && exists(input_path + file_name2)) file_name2 = input_path + file_name2;
+  } else {
+    std::cout << "Usage: " << argv[0] << " <settings file>. Otherwise settings.xml in the current directory is used\n"
+              << "       " << argv[0] << " <file1> <file2> <width> <height> [<counter>] <output path> [<alpha> <sigma>]" << std::endl;
+    return 0;
+  }
+
+  OpticalFlow2D optical_flow;
+  DataSize3 data_size = {width, height, 1};
+  if (!optical_flow.Initialize(data_size, data_constancy)) return 1;
+
+  Data2D frame_0, frame_1;
+  const bool loaded = eight_bit ? (frame_0.ReadRAWFromFileU8(file_name1.c_str(), width, height) &&
+                                   frame_1.ReadRAWFromFileU8(file_name2.c_str(), width, height))
+                                : (frame_0.ReadRAWFromFileF32(file_name1.c_str(), width, height) &&
+                                   frame_1.ReadRAWFromFileF32(file_name2.c_str(), width, height));
+  if (!loaded) return 2;
+
+  Data2D flow_u(width, height), flow_v(width, height);
+  optical_flow.silent = true;
+
+  OperationParameters params;
+  params.PushValuePtr("warp_levels_count", &warp_levels_count);
+  params.PushValuePtr("warp_scale_factor", &warp_scale_factor);
+  params.PushValuePtr("outer_iterations_count", &outer_iterations_count);
+  params.PushValuePtr("inner_iterations_count", &inner_iterations_count);
+  params.PushValuePtr("equation_alpha", &equation_alpha);
+  params.PushValuePtr("equation_smoothness", &equation_smoothness);
+  params.PushValuePtr("equation_data", &equation_data);
+  params.PushValuePtr("median_radius", &median_radius);
+  params.PushValuePtr("gaussian_sigma", &gaussian_sigma);
+
+  optical_flow.ComputeFlow(frame_0, frame_1, flow_u, flow_v, params);
+
+  const string suffix = "-" + std::to_string(width) + "-" + std::to_string(height) + ".raw";
+  flow_u.WriteRAWToFileF32((output_path + counter + "flow-u" + suffix).c_str());
+  flow_v.WriteRAWToFileF32((output_path + counter + "flow-v" + suffix).c_str());
+  {  // amp-W-H.raw: flow magnitude (src/utils/io_utils.cpp:68-90)
+    Data2D amp(width, height);
+    for (size_t y = 0; y < height; ++y)
+      for (size_t x = 0; x < width; ++x) {
+        const float a = flow_u.Data(x, y), b = flow_v.Data(x, y);
+        amp.Data(x, y) = std::sqrt(a * a + b * b);
+      }
+    amp.WriteRAWToFileF32((output_path + counter + "amp" + suffix).c_str());
+  }
+  optical_flow.Destroy();
+  return 0;
+}

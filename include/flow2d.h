@@ -145,6 +145,12 @@ FLOW2D_API int flow2d_stage_median(flow2d_handle* h, const float* d_in, float* d
 FLOW2D_API int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b, float* d_out,
                             size_t w, size_t h_, size_t radius);
 
+/* Page-locked host memory for frames / flow fields, so the H2D / D2H copies of flow2d_compute are
+ * plain DMA (the reference's optional ALLOCATE_PINNED_MEMORY path, src/data_types/data2d.cpp:52-60).
+ * flow2d_host_alloc returns NULL when there is no device or the allocation fails. */
+FLOW2D_API void* flow2d_host_alloc(size_t bytes);
+FLOW2D_API void flow2d_host_free(void* p);
+
 /* Library identification: "flow2d-b200 <version> sm_100a". */
 FLOW2D_API const char* flow2d_version(void);
 

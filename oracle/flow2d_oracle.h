@@ -6,11 +6,13 @@
  * into, imported by or called from the product library.  Only tests/, the smoke check
  * in __graft_entry__.py and bench.py's cpu_baseline leg may use it.
  *
- * Parity status: the reference ships no tests, golden vectors or fixtures for this path
+ * Parity status: PINNED.  The reference ships no tests, golden vectors or fixtures for this path
  * (SURVEY.md F6), so this restatement is pinned against the reference's OWN CUDA build
- * (oracle/_ref, built by oracle/Makefile from the sources under /root/reference and run
- * on the GPU box): per-kernel, by driving the reference PTX kernels on identical buffers
- * (oracle/ref_stage.cpp), and end to end on the rub pair (tests/golden/).
+ * (oracle/_ref, built by oracle/Makefile from the sources under /root/reference and run on a
+ * B200): operator by operator through the reference's CudaOperation*2D::Execute on identical
+ * buffers (oracle/ref_harness.cpp) and end to end on the bundled rub pair with both reference
+ * parameter sets.  Result: bit-exact (tests/test_golden_cpu.py on the committed outputs in
+ * tests/golden/, tests/test_reference_gpu.py live on the GPU box).
  *
  * Every function cites the reference file:line it follows.  Floating-point expression
  * trees (which mul/add pairs are fused) follow the reference kernels as compiled by
