@@ -22,7 +22,7 @@ void launch_add_median(cudaStream_t st, const float* const* a, const float* cons
 void launch_add(cudaStream_t st, float* a, const float* b, int w, int h, int pitch);
 
 // ---- solve.cu ----
-constexpr int kSolveLW = 64, kSolveLH = 64;  // shared-memory region of one CTA (output tile + halo)
+constexpr int kSolveLW = 64, kSolveLH = 48;  // shared-memory region of one CTA (output tile + halo)
 
 struct SolveArgs {
   const float *fx, *fy, *ft;      // brightness derivatives of the level (launch_derivatives)

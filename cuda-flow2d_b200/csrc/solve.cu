@@ -6,19 +6,30 @@
 // (src/cuda_operations/2d/cuda_operation_solve_2d.cpp:229-299), with identical results:
 // the reference's scheme is a double-buffered JACOBI sweep (all neighbour reads from the previous
 // iterate) with one Gauss-Seidel coupling inside the pixel (dv' uses du'), no relaxation factor.
-// Jacobi is tiling independent, so S sweeps can be run on a shared-memory tile with an S-pixel
-// halo and give bit-identical values to S separate global sweeps.
 //
-// One CTA = 512 threads = one 64x64 region L of the level (output tile O plus halo).  A thread owns
-// two 1x4 pixel strips for the whole pass; everything that is constant per pixel during the sweeps
-// lives in registers or in thread-private shared-memory planes, and only s_u = u+du, s_v = v+dv are
-// exchanged: x neighbours by warp shuffle, y neighbours through double-buffered shared planes.
+// Temporal blocking.  One CTA = 768 threads = one 64x48 region of the level; a thread owns one 1x4
+// pixel strip for the whole pass.  EVERY cell of the region is updated in EVERY sweep, without any
+// activity mask: a cell's value after sweep k is exact iff its inputs were exact, so under Jacobi
+// the set of exact cells simply shrinks by one ring per sweep from the region's edge (phi needs one
+// ring, the edge weights another, then one per sweep).  With a halo of S+1 cells the output tile is
+// exact after S sweeps and bit-identical to S separate global sweeps; what happens in the rings
+// outside it is never stored.  At the image border nothing shrinks: the reference's mirrored
+// border (index -1 -> 1, n -> n-2) means "the mirrored neighbour IS the opposite neighbour", which
+// is a row-offset choice in y and a register select in x (only in CTAs that touch the border).
+// Cells of a border region that lie outside the image are made inert (zero weights, ksi = 0,
+// denominator 1) so that they stay finite and cheap.
 //
-//   phase A  load u, v, du, dv (strip-wise float4) -> registers + shared planes; fx, fy, ft -> regs
-//   phase B  phi on L minus apron, ksi; phi -> shared plane         (or load phi/ksi of an earlier pass)
-//   phase C  edge weights, sumH, the two denominators, -J12, -J13, -J23
-//   phase D  S sweeps; sweep k updates O grown by S-k pixels (clipped to the image)
-//   phase E  store du, dv (and phi, ksi if a later pass of the same outer iteration needs them)
+// Everything that is constant per pixel during the sweeps lives in registers or in thread-private
+// shared-memory planes (conflict-free LDS.128); only s_u = u+du, s_v = v+dv are exchanged:
+// x neighbours by warp shuffle, y neighbours through double-buffered shared planes, one
+// __syncthreads per sweep.
+//
+//   phase A  all global loads of the pass (float4 per strip); motion tensor and ksi -> planes
+//   phase B  u/v/du/dv published for the neighbour rows; phi
+//            (or phi/ksi of an earlier pass of the same outer iteration are loaded)
+//   phase C  edge weights, sumH, the two denominators and their fast-path reciprocals
+//   phase D  S Jacobi sweeps
+//   phase E  store du, dv of the output tile
 //
 // "Resident" mode: if the whole level fits one region, a single CTA runs ALL outer iterations and
 // all inner sweeps of the level without leaving the SM (grid = 1).
@@ -26,21 +37,21 @@
 
 namespace flow2d {
 
-constexpr int LW = kSolveLW, LH = kSolveLH;  // 64 x 64
-constexpr int NT = 512;
-constexpr int PL = LW * LH;  // floats per shared plane
+constexpr int LW = kSolveLW, LH = kSolveLH;  // 64 x 48
+constexpr int NT = LH * (LW / 4);            // one thread per 1x4 strip: 768 threads, <= 80 registers each
+constexpr int PL = LW * LH;                  // floats per shared plane
 
-// shared planes
+// shared planes (14 x 12 KiB = 168 KiB; the rest of the 228 KiB stays L1)
 enum {
-  P_U = 0, P_V, P_DU, P_DV,        // phase A/B: neighbour access for phi
-  P_PHI,                           // phase B/C
-  P_SU0, P_SV0, P_SU1, P_SV1,      // phase D: double-buffered s_u, s_v
-  P_NJ13, P_NJ23,                  // thread-private: -J13, -J23
+  P_SU0 = 0, P_SV0, P_SU1, P_SV1,   // phase D: double-buffered s_u, s_v (read by the rows above/below)
+  P_EYP, P_EYM,                     // thread-private from here on: y edge weights
+  P_DENU, P_DENV, P_RU, P_RV,       // the two denominators and their fast-path reciprocals
+  P_NJ13, P_NJ23, P_KSI, P_NJ12,
   kNumPlanes,
-  // thread-private planes aliased onto the phase A/B planes (dead after the barrier that ends phase B)
-  P_EYP = P_U, P_EYM = P_V, P_DENU = P_DU, P_DENV = P_DV,
-  // phase B -> C hand-over of J11, J22 through planes that are first written by sweep 1
-  P_J11 = P_SU1, P_J22 = P_SV1
+  // phase B planes, aliased onto planes that are first written after the barrier ending phase B
+  P_U = P_EYP, P_V = P_EYM, P_DU = P_DENU, P_DV = P_DENV,
+  P_PHI = P_SU1,                    // read in phase C; sweep 1 is the first writer of SU1
+  P_J11 = P_RU, P_J22 = P_RV        // thread-private hand-over A -> C
 };
 
 size_t solve_pass_smem_bytes() { return sizeof(float) * PL * kNumPlanes; }
@@ -53,327 +64,425 @@ __device__ __forceinline__ void unpack(const float4& q, float (&v)[4]) {
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
 }
 
-// Own strip (gx..gx+3, gy) of a global plane.  Cells outside the image are clamped to valid
-// memory; their values are never used in arithmetic (see nb_* below).
-__device__ __forceinline__ void load_strip(const float* __restrict__ p, int gx, int gy, int w, int h, int pitch,
-                                           float (&v)[4]) {
-  const int my = min(max(gy, 0), h - 1);
-  const float* row = p + (size_t)my * pitch;
-  if (gx >= 0 && gx + 3 < w) {
-    unpack(ld4(row + gx), v);
+// Where this thread's strip lives in a global plane.  Cells outside the image are clamped to valid
+// memory; their values never reach a cell of the output tile.
+struct StripAddr {
+  size_t off;     // row * pitch + gx               (vector path)
+  size_t row;     // row * pitch                    (scalar path)
+  int cx[4];      // clamped columns                (scalar path)
+  bool interior;  // the strip lies completely inside [0, w)
+};
+__device__ __forceinline__ void load_strip(const float* __restrict__ p, const StripAddr& s, float (&v)[4]) {
+  if (s.interior) {
+    unpack(ld4(p + s.off), v);
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = row[min(max(gx + i, 0), w - 1)];
+    for (int i = 0; i < 4; i++) v[i] = p[s.row + s.cx[i]];
   }
 }
 
-// Neighbour selection with the reference's mirrored border (index -1 -> 1, n -> n-2): at the image
-// border the mirrored neighbour IS the opposite neighbour, so no out-of-image value is ever used.
-__device__ __forceinline__ float nb_lo(bool at_lo_border, float lo, float hi) { return at_lo_border ? hi : lo; }
-__device__ __forceinline__ float nb_hi(bool at_hi_border, float lo, float hi) { return at_hi_border ? lo : hi; }
+// ---- IEEE division by a divisor that is reused many times ------------------------------------
+// div.rn.f32 is implemented by the hardware as
+//     r0 = MUFU.RCP(d); e = fma(-d, r0, 1); r = fma(r0, e, r0);        (refined reciprocal)
+//     q0 = a*r; rem = fma(-d, q0, a); q = fma(r, rem, q0)               (fast path)
+// plus a slow path taken when FCHK flags extreme exponents.  The reciprocal part depends on the
+// divisor only, so it is hoisted out of the sweeps; the quotient part is repeated verbatim, which
+// gives the bits of div.rn whenever the fast path applies.  Guard: divisor and dividend within
+// 2^-60 .. 2^60 (far inside FCHK's safe range), or a zero dividend (quotient = a*r = +-0 with the
+// right sign).  Everything else takes the plain `a / d`.
+__device__ __forceinline__ bool in_fast_range(float x) {
+  const unsigned e = (__float_as_uint(x) >> 23) & 0xffu;
+  return (e - 67u) < 120u;
+}
+__device__ __forceinline__ float fast_path_rcp(float d) {  // 0 = "divisor not safe, use a / d"
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d));
+  const float e = fmaf(-d, r0, 1.f);
+  const float r = fmaf(r0, e, r0);
+  return in_fast_range(d) ? r : 0.f;
+}
+// Four quotients.  Common case (all dividends in range): 12 FMA-pipe instructions and one branch.
+__device__ __forceinline__ void div_rn4(const float (&a)[4], const float (&d)[4], const float (&r)[4], bool den_ok,
+                                        float (&q)[4]) {
+  float q0[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    q0[i] = a[i] * r[i];
+    q[i] = fmaf(r[i], fmaf(-d[i], q0[i], a[i]), q0[i]);
+  }
+  const float lo = fminf(fminf(fabsf(a[0]), fabsf(a[1])), fminf(fabsf(a[2]), fabsf(a[3])));
+  const float hi = fmaxf(fmaxf(fabsf(a[0]), fabsf(a[1])), fmaxf(fabsf(a[2]), fabsf(a[3])));
+  if (!(den_ok && lo >= 0x1p-60f && hi < 0x1p60f)) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (a[i] == 0.f && r[i] != 0.f) q[i] = q0[i];
+      else if (!(r[i] != 0.f && in_fast_range(a[i]))) q[i] = a[i] / d[i];
+    }
+  }
+}
+// Same with one divisor for all four dividends.
+__device__ __forceinline__ void div_rn4(const float (&a)[4], float d, float r, float (&q)[4]) {
+  const float dd[4] = {d, d, d, d}, rr[4] = {r, r, r, r};
+  div_rn4(a, dd, rr, r != 0.f, q);
+}
 
-template <bool GRAD>
-__global__ void __launch_bounds__(NT, 1) solve_pass_kernel(const SolveArgs a) {
-  extern __shared__ __align__(16) float sm[];
+struct Strip {  // per-thread state that lives in registers during the sweeps
+  float uc[4], vc[4], dv[4];
+  float su[4], sv[4];
+  float ex[5];  // x edge weights: ex[i] lies between pixels x-1+i and x+i
+  bool den_ok;  // all eight denominators of the strip are safe for the fast division path
+};
+
+// x neighbours of strip element i: inside the strip from registers, at its ends from the adjacent
+// lanes (L, R); at the image border (BORDER CTAs only) the mirrored neighbour is the opposite one.
+template <bool BORDER>
+__device__ __forceinline__ void x_nb(const float (&c)[4], float L, float R, int i, bool x_lo, int i_hi, float& l,
+                                     float& r) {
+  l = i > 0 ? c[i - 1] : L;
+  r = i < 3 ? c[i + 1] : R;
+  if (BORDER) {
+    const float l0 = l;
+    l = (x_lo && i == 0) ? r : l;
+    r = (i == i_hi) ? l0 : r;
+  }
+}
+
+template <bool GRAD, bool BORDER>
+__device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   const int tid = threadIdx.x;
-  const int lane_c = tid & 15;  // strip column within the region
-  const int lx = 4 * lane_c;
+  const int row = tid >> 4;       // row of the region
+  const int lx = 4 * (tid & 15);  // first column of the strip within the region
   const int w = a.w, h = a.h, pitch = a.pitch;
 
   const int ox0 = blockIdx.x * a.ow, oy0 = blockIdx.y * a.oh;
   const int ox1 = min(w, ox0 + a.ow), oy1 = min(h, oy0 + a.oh);
-  const int lx0 = ox0 - a.halo_x, ly0 = oy0 - a.halo_y;
-  const int gx = lx0 + lx;  // multiple of 4
-
-  // per-strip constants
-  int gy[2], soff[2];
-  gy[0] = ly0 + (tid >> 4);
-  gy[1] = gy[0] + 32;
-  soff[0] = (tid >> 4) * LW + lx;
-  soff[1] = soff[0] + 32 * LW;
-
-  // per-pixel flags: inside the image and inside the region minus its 1-cell apron
-  bool live[2][4];
+  const int gx = ox0 - a.halo_x + lx;  // multiple of 4
+  const int gy = oy0 - a.halo_y + row;
+  const int soff = row * LW + lx;
+  // Neighbour rows.  Image border: the mirrored neighbour is the opposite neighbour.  Rows 0 and
+  // LH-1 of the region have no neighbour row in shared memory (they are never exact anyway).
+  int up_off = row > 0 ? -LW : LW, dn_off = row < LH - 1 ? LW : -LW;
+  if (BORDER) {
+    if (gy == 0 && row < LH - 1) up_off = LW;
+    if (gy == h - 1 && row > 0) dn_off = -LW;
+  }
+  const bool x_lo = BORDER && gx == 0;        // only element 0 of a strip can be x == 0 (gx % 4 == 0)
+  const int i_hi = BORDER ? w - 1 - gx : -1;  // element index of x == w-1 in this strip, if 0..3
+  bool inside[4];                             // cells outside the image exist only in BORDER CTAs
 #pragma unroll
-  for (int s = 0; s < 2; s++)
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int x = gx + i, y = gy[s], lxx = lx + i, lyy = y - ly0;
-      live[s][i] = x >= 0 && x < w && y >= 0 && y < h && lxx >= 1 && lxx <= LW - 2 && lyy >= 1 && lyy <= LH - 2;
-    }
+  for (int i = 0; i < 4; i++) inside[i] = !BORDER || (gx + i >= 0 && gx + i < w && gy >= 0 && gy < h);
 
-  const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
-  const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
-
-  float uc[2][4], vc[2][4], du[2][4], dv[2][4];
+  StripAddr sa;
+  {
+    const int my = min(max(gy, 0), h - 1);
+    sa.row = (size_t)my * pitch;
+    sa.off = sa.row + gx;
+    sa.interior = gx >= 0 && gx + 3 < w;
 #pragma unroll
-  for (int s = 0; s < 2; s++) {
-    load_strip(a.u, gx, gy[s], w, h, pitch, uc[s]);
-    load_strip(a.v, gx, gy[s], w, h, pitch, vc[s]);
-    if (a.du_in) {
-      load_strip(a.du_in, gx, gy[s], w, h, pitch, du[s]);
-      load_strip(a.dv_in, gx, gy[s], w, h, pitch, dv[s]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++) du[s][i] = dv[s][i] = 0.f;
-    }
+    for (int i = 0; i < 4; i++) sa.cx[i] = min(max(gx + i, 0), w - 1);
   }
 
-  float ksi[2][4], nJ12[2][4], su[2][4], sv[2][4], ex[2][5];
+  Strip t;
+  float du[4];  // increment in u: live in phases A-C and as the sweeps' result, not across the sweeps
+  load_strip(a.u, sa, t.uc);
+  load_strip(a.v, sa, t.vc);
+  if (a.du_in) {
+    load_strip(a.du_in, sa, du);
+    load_strip(a.dv_in, sa, t.dv);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) du[i] = t.dv[i] = 0.f;
+  }
+
+  const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
+  const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
+  const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
 
   for (int outer = 0; outer < a.outer; ++outer) {
-    // ---------------- phase A: publish u, v, du, dv ----------------
-    if (outer > 0) __syncthreads();  // previous iteration's readers of the aliased planes are done
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      st4(sm + P_U * PL + soff[s], uc[s]);
-      st4(sm + P_V * PL + soff[s], vc[s]);
-      st4(sm + P_DU * PL + soff[s], du[s]);
-      st4(sm + P_DV * PL + soff[s], dv[s]);
-    }
-    __syncthreads();
+    // (the sweep loop of the previous outer iteration ended with a barrier: every plane is free)
+    // resident mode: du of the previous outer iteration comes back from this thread's own store
+    if (outer > 0) load_strip(a.du_out, sa, du);
 
-    // ---------------- phase B: phi, ksi ----------------
-    float phi[2][4];
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      const int y = gy[s];
-      const bool y_lo = (y == 0), y_hi = (y == h - 1);
-      float fx[4], fy[4], ft[4];
-      load_strip(a.fx, gx, y, w, h, pitch, fx);
-      load_strip(a.fy, gx, y, w, h, pitch, fy);
-      load_strip(a.ft, gx, y, w, h, pitch, ft);
-
+    // ------ phase A: remaining loads; motion tensor (solve_2d.cu:324-329 / 879-884); ksi (176-196) ------
+    float phi[4];
+    {
+      float fx[4], fy[4], ft[4], ksi[4];
+      load_strip(a.fx, sa, fx);
+      load_strip(a.fy, sa, fy);
+      load_strip(a.ft, sa, ft);
       if (a.phi_in) {
-        load_strip(a.phi_in, gx, y, w, h, pitch, phi[s]);
-        load_strip(a.ksi_in, gx, y, w, h, pitch, ksi[s]);
-      } else {
-        // x neighbours of the strip ends come from the adjacent lanes
-        const float uL = __shfl_up_sync(0xffffffffu, uc[s][3], 1), uR = __shfl_down_sync(0xffffffffu, uc[s][0], 1);
-        const float vL = __shfl_up_sync(0xffffffffu, vc[s][3], 1), vR = __shfl_down_sync(0xffffffffu, vc[s][0], 1);
-        const float duL = __shfl_up_sync(0xffffffffu, du[s][3], 1), duR = __shfl_down_sync(0xffffffffu, du[s][0], 1);
-        const float dvL = __shfl_up_sync(0xffffffffu, dv[s][3], 1), dvR = __shfl_down_sync(0xffffffffu, dv[s][0], 1);
-        float uU[4], uD[4], vU[4], vD[4], duU[4], duD[4], dvU[4], dvD[4];
-        // rows 0 and LH-1 of the region are apron (never live): clamp their neighbour row
-        const int up = soff[s] - ((tid >> 4) + 32 * s > 0 ? LW : 0);
-        const int dn = soff[s] + ((tid >> 4) + 32 * s < LH - 1 ? LW : 0);
-        unpack(ld4(sm + P_U * PL + up), uU); unpack(ld4(sm + P_V * PL + up), vU);
-        unpack(ld4(sm + P_DU * PL + up), duU); unpack(ld4(sm + P_DV * PL + up), dvU);
-        unpack(ld4(sm + P_U * PL + dn), uD); unpack(ld4(sm + P_V * PL + dn), vD);
-        unpack(ld4(sm + P_DU * PL + dn), duD); unpack(ld4(sm + P_DV * PL + dn), dvD);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          phi[s][i] = 0.f;
-          ksi[s][i] = 0.f;
-          if (live[s][i]) {
-            const int x = gx + i;
-            const bool x_lo = (x == 0), x_hi = (x == w - 1);
-            const float ul_raw = i > 0 ? uc[s][i - 1] : uL, ur_raw = i < 3 ? uc[s][i + 1] : uR;
-            const float vl_raw = i > 0 ? vc[s][i - 1] : vL, vr_raw = i < 3 ? vc[s][i + 1] : vR;
-            const float dul_raw = i > 0 ? du[s][i - 1] : duL, dur_raw = i < 3 ? du[s][i + 1] : duR;
-            const float dvl_raw = i > 0 ? dv[s][i - 1] : dvL, dvr_raw = i < 3 ? dv[s][i + 1] : dvR;
-            const float u_l = nb_lo(x_lo, ul_raw, ur_raw), u_r = nb_hi(x_hi, ul_raw, ur_raw);
-            const float v_l = nb_lo(x_lo, vl_raw, vr_raw), v_r = nb_hi(x_hi, vl_raw, vr_raw);
-            const float du_l = nb_lo(x_lo, dul_raw, dur_raw), du_r = nb_hi(x_hi, dul_raw, dur_raw);
-            const float dv_l = nb_lo(x_lo, dvl_raw, dvr_raw), dv_r = nb_hi(x_hi, dvl_raw, dvr_raw);
-            const float u_u = nb_lo(y_lo, uU[i], uD[i]), u_d = nb_hi(y_hi, uU[i], uD[i]);
-            const float v_u = nb_lo(y_lo, vU[i], vD[i]), v_d = nb_hi(y_hi, vU[i], vD[i]);
-            const float du_u = nb_lo(y_lo, duU[i], duD[i]), du_d = nb_hi(y_hi, duU[i], duD[i]);
-            const float dv_u = nb_lo(y_lo, dvU[i], dvD[i]), dv_d = nb_hi(y_hi, dvU[i], dvD[i]);
-            // solve_2d.cu:141-162
-            const float dux = (((u_r - u_l) + du_r) - du_l) / hx2;
-            const float duy = (((u_d - u_u) + du_d) - du_u) / hy2;
-            const float dvx = (((v_r - v_l) + dv_r) - dv_l) / hx2;
-            const float dvy = (((v_d - v_u) + dv_d) - dv_u) / hy2;
-            float t = duy * duy;
-            t = fmaf(dux, dux, t);
-            t = fmaf(dvx, dvx, t);
-            t = fmaf(dvy, dvy, t);
-            t = fmaf(a.e_smooth, a.e_smooth, t);
-            const float r = sqrtf(t);
-            phi[s][i] = 1.f / (r + r);
-            // solve_2d.cu:176-196 (always the brightness tensor, also in gradient mode)
-            const float j11 = fx[i] * fx[i], j22 = fy[i] * fy[i], j12 = fx[i] * fy[i];
-            const float j13 = fx[i] * ft[i], j23 = fy[i] * ft[i];
-            const float d_u = du[s][i], d_v = dv[s][i];
-            const float ta = j13 + fmaf(j11, d_u, j12 * d_v);
-            const float tb = j23 + fmaf(j12, d_u, j22 * d_v);
-            const float tc = fmaf(ft[i], ft[i], fmaf(j13, d_u, j23 * d_v));
-            float sq = fmaf(d_u, ta, d_v * tb) + tc;
-            sq = sq * ((sq > 0.f) ? 1.f : 0.f);
-            const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
-            ksi[s][i] = 1.f / (q + q);
-          }
-        }
+        load_strip(a.phi_in, sa, phi);
+        load_strip(a.ksi_in, sa, ksi);
       }
-      // motion tensor of the sweep (solve_2d.cu:324-329 / 879-884)
-      {
-        float J11[4], J22[4], nJ13[4], nJ23[4];
-        if (GRAD) {
-          float j12[4];
-          load_strip(a.J[0], gx, y, w, h, pitch, J11);
-          load_strip(a.J[1], gx, y, w, h, pitch, J22);
-          load_strip(a.J[2], gx, y, w, h, pitch, j12);
-          load_strip(a.J[3], gx, y, w, h, pitch, nJ13);
-          load_strip(a.J[4], gx, y, w, h, pitch, nJ23);
-#pragma unroll
-          for (int i = 0; i < 4; i++) { nJ12[s][i] = -j12[i]; nJ13[i] = -nJ13[i]; nJ23[i] = -nJ23[i]; }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            J11[i] = fx[i] * fx[i];
-            J22[i] = fy[i] * fy[i];
-            nJ12[s][i] = -(fx[i] * fy[i]);
-            nJ13[i] = -(fx[i] * ft[i]);
-            nJ23[i] = -(fy[i] * ft[i]);
-          }
-        }
-        st4(sm + P_J11 * PL + soff[s], J11);
-        st4(sm + P_J22 * PL + soff[s], J22);
-        st4(sm + P_NJ13 * PL + soff[s], nJ13);
-        st4(sm + P_NJ23 * PL + soff[s], nJ23);
-      }
-      st4(sm + P_PHI * PL + soff[s], phi[s]);
-    }
-    __syncthreads();  // phi published; P_U..P_DV are dead from here on
-
-    // ---------------- phase C: weights and denominators ----------------
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-      const int y = gy[s];
-      const bool y_lo = (y == 0), y_hi = (y == h - 1);
-      const float pL = __shfl_up_sync(0xffffffffu, phi[s][3], 1), pR = __shfl_down_sync(0xffffffffu, phi[s][0], 1);
-      float pU[4], pD[4];
-      unpack(ld4(sm + P_PHI * PL + soff[s] - ((tid >> 4) + 32 * s > 0 ? LW : 0)), pU);
-      unpack(ld4(sm + P_PHI * PL + soff[s] + ((tid >> 4) + 32 * s < LH - 1 ? LW : 0)), pD);
-      const float wyp = hy_2 * ((y < h - 1) ? 1.f : 0.f), wym = hy_2 * ((y > 0) ? 1.f : 0.f);
-      float eyp[4], eym[4], denU[4], denV[4], J11[4], J22[4];
-      unpack(ld4(sm + P_J11 * PL + soff[s]), J11);
-      unpack(ld4(sm + P_J22 * PL + soff[s]), J22);
+      float J11[4], J22[4], J12[4], J13[4], J23[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int x = gx + i;
-        const bool x_lo = (x == 0), x_hi = (x == w - 1);
-        const float pl_raw = i > 0 ? phi[s][i - 1] : pL, pr_raw = i < 3 ? phi[s][i + 1] : pR;
-        const float p_l = nb_lo(x_lo, pl_raw, pr_raw), p_r = nb_hi(x_hi, pl_raw, pr_raw);
-        const float p_u = nb_lo(y_lo, pU[i], pD[i]), p_d = nb_hi(y_hi, pU[i], pD[i]);
-        const float pc = phi[s][i];
-        // solve_2d.cu:333-349
-        const float wxp = hx_2 * ((x < w - 1) ? 1.f : 0.f), wxm = hx_2 * ((x > 0) ? 1.f : 0.f);
-        const float axp = wxp * ((p_r + pc) * 0.5f);
-        const float axm = wxm * ((p_l + pc) * 0.5f);
-        eyp[i] = wyp * ((p_d + pc) * 0.5f);
-        eym[i] = wym * ((p_u + pc) * 0.5f);
-        // axm(x) == axp(x-1) bit for bit for x >= 1 (same products, commuted add), so only the
-        // strip's first axm is kept separately
-        if (i == 0) ex[s][0] = axm;
-        ex[s][i + 1] = axp;
-        const float sumH = ((axp + axm) + eyp[i]) + eym[i];
-        denU[i] = fmaf(J11[i], ksi[s][i], sumH);
-        denV[i] = fmaf(J22[i], ksi[s][i], sumH);
-        su[s][i] = uc[s][i] + du[s][i];
-        sv[s][i] = vc[s][i] + dv[s][i];
+        J11[i] = fx[i] * fx[i];
+        J22[i] = fy[i] * fy[i];
+        J12[i] = fx[i] * fy[i];
+        J13[i] = fx[i] * ft[i];
+        J23[i] = fy[i] * ft[i];
       }
-      st4(sm + P_EYP * PL + soff[s], eyp);
-      st4(sm + P_EYM * PL + soff[s], eym);
-      st4(sm + P_DENU * PL + soff[s], denU);
-      st4(sm + P_DENV * PL + soff[s], denV);
-      st4(sm + P_SU0 * PL + soff[s], su[s]);
-      st4(sm + P_SV0 * PL + soff[s], sv[s]);
-      if (a.phi_out && !a.phi_in) {
+      if (!a.phi_in) {
+        // own pixel only; always the brightness tensor, also in gradient mode
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float d_u = du[i], d_v = t.dv[i];
+          const float ta = J13[i] + fmaf(J11[i], d_u, J12[i] * d_v);
+          const float tb = J23[i] + fmaf(J12[i], d_u, J22[i] * d_v);
+          const float tc = fmaf(ft[i], ft[i], fmaf(J13[i], d_u, J23[i] * d_v));
+          float sq = fmaf(d_u, ta, d_v * tb) + tc;
+          sq = sq * ((sq > 0.f) ? 1.f : 0.f);
+          const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
+          ksi[i] = 1.f / (q + q);
+        }
+      }
+      if (BORDER) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) ksi[i] = inside[i] ? ksi[i] : 0.f;
+      }
+      st4(sm + P_KSI * PL + soff, ksi);
+      if (GRAD) {
+        load_strip(a.J[0], sa, J11);
+        load_strip(a.J[1], sa, J22);
+        load_strip(a.J[2], sa, J12);
+        load_strip(a.J[3], sa, J13);
+        load_strip(a.J[4], sa, J23);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) { J12[i] = -J12[i]; J13[i] = -J13[i]; J23[i] = -J23[i]; }
+      st4(sm + P_J11 * PL + soff, J11);
+      st4(sm + P_J22 * PL + soff, J22);
+      st4(sm + P_NJ12 * PL + soff, J12);
+      st4(sm + P_NJ13 * PL + soff, J13);
+      st4(sm + P_NJ23 * PL + soff, J23);
+    }
+
+    if (!a.phi_in) {
+      // ---------------- phase B: phi (solve_2d.cu:141-162) ----------------
+      st4(sm + P_U * PL + soff, t.uc);
+      st4(sm + P_V * PL + soff, t.vc);
+      st4(sm + P_DU * PL + soff, du);
+      st4(sm + P_DV * PL + soff, t.dv);
+      __syncthreads();
+      float dux[4], duy[4], dvx[4], dvy[4], num[4];
+      {
+        float nU[4], nD[4];
+        unpack(ld4(sm + P_U * PL + soff + up_off), nU);
+        unpack(ld4(sm + P_U * PL + soff + dn_off), nD);
+#pragma unroll
+        for (int i = 0; i < 4; i++) num[i] = nD[i] - nU[i];
+        unpack(ld4(sm + P_DU * PL + soff + up_off), nU);
+        unpack(ld4(sm + P_DU * PL + soff + dn_off), nD);
+#pragma unroll
+        for (int i = 0; i < 4; i++) num[i] = (num[i] + nD[i]) - nU[i];
+        div_rn4(num, hy2, rhy2, duy);
+        unpack(ld4(sm + P_V * PL + soff + up_off), nU);
+        unpack(ld4(sm + P_V * PL + soff + dn_off), nD);
+#pragma unroll
+        for (int i = 0; i < 4; i++) num[i] = nD[i] - nU[i];
+        unpack(ld4(sm + P_DV * PL + soff + up_off), nU);
+        unpack(ld4(sm + P_DV * PL + soff + dn_off), nD);
+#pragma unroll
+        for (int i = 0; i < 4; i++) num[i] = (num[i] + nD[i]) - nU[i];
+        div_rn4(num, hy2, rhy2, dvy);
+      }
+      {
+        const float uL = __shfl_up_sync(0xffffffffu, t.uc[3], 1), uR = __shfl_down_sync(0xffffffffu, t.uc[0], 1);
+        const float dL = __shfl_up_sync(0xffffffffu, du[3], 1), dR = __shfl_down_sync(0xffffffffu, du[0], 1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          float l, r, dl, dr;
+          x_nb<BORDER>(t.uc, uL, uR, i, x_lo, i_hi, l, r);
+          x_nb<BORDER>(du, dL, dR, i, x_lo, i_hi, dl, dr);
+          num[i] = ((r - l) + dr) - dl;
+        }
+        div_rn4(num, hx2, rhx2, dux);
+      }
+      {
+        const float vL = __shfl_up_sync(0xffffffffu, t.vc[3], 1), vR = __shfl_down_sync(0xffffffffu, t.vc[0], 1);
+        const float dL = __shfl_up_sync(0xffffffffu, t.dv[3], 1), dR = __shfl_down_sync(0xffffffffu, t.dv[0], 1);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          float l, r, dl, dr;
+          x_nb<BORDER>(t.vc, vL, vR, i, x_lo, i_hi, l, r);
+          x_nb<BORDER>(t.dv, dL, dR, i, x_lo, i_hi, dl, dr);
+          num[i] = ((r - l) + dr) - dl;
+        }
+        div_rn4(num, hx2, rhx2, dvx);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float s = duy[i] * duy[i];
+        s = fmaf(dux[i], dux[i], s);
+        s = fmaf(dvx[i], dvx[i], s);
+        s = fmaf(dvy[i], dvy[i], s);
+        s = fmaf(a.e_smooth, a.e_smooth, s);
+        const float r = sqrtf(s);
+        phi[i] = 1.f / (r + r);
+      }
+    }
+    st4(sm + P_PHI * PL + soff, phi);
+    __syncthreads();  // phi published; every reader of P_U..P_DV is done, so their aliases are free
+
+    // ---------------- phase C: weights and denominators (solve_2d.cu:333-349, 363, 367) ----------------
+    {
+      const float pL = __shfl_up_sync(0xffffffffu, phi[3], 1), pR = __shfl_down_sync(0xffffffffu, phi[0], 1);
+      float pU[4], pD[4], J11[4], J22[4], ksi[4];
+      unpack(ld4(sm + P_PHI * PL + soff + up_off), pU);
+      unpack(ld4(sm + P_PHI * PL + soff + dn_off), pD);
+      unpack(ld4(sm + P_J11 * PL + soff), J11);
+      unpack(ld4(sm + P_J22 * PL + soff), J22);
+      unpack(ld4(sm + P_KSI * PL + soff), ksi);
+      if (a.phi_out && !a.phi_in) {  // a later pass of this outer iteration reloads the robust weights
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const int x = gx + i;
-          if (x >= ox0 && x < ox1 && y >= oy0 && y < oy1) {
-            a.phi_out[(size_t)y * pitch + x] = phi[s][i];
-            a.ksi_out[(size_t)y * pitch + x] = ksi[s][i];
+          if (x >= ox0 && x < ox1 && gy >= oy0 && gy < oy1) {
+            a.phi_out[(size_t)gy * pitch + x] = phi[i];
+            a.ksi_out[(size_t)gy * pitch + x] = ksi[i];
           }
         }
       }
+      // Neumann boundary through zero weights (solve_2d.cu:337-340)
+      float wyp = hy_2, wym = hy_2;
+      if (BORDER) {
+        wyp = hy_2 * ((gy < h - 1) ? 1.f : 0.f);
+        wym = hy_2 * ((gy > 0) ? 1.f : 0.f);
+      }
+      float eyp[4], eym[4], denU[4], denV[4], rU[4], rV[4];
+      t.den_ok = true;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float p_l, p_r;
+        x_nb<BORDER>(phi, pL, pR, i, x_lo, i_hi, p_l, p_r);
+        const float pc = phi[i];
+        float wxp = hx_2, wxm = hx_2;
+        if (BORDER) {
+          wxp = hx_2 * ((gx + i < w - 1) ? 1.f : 0.f);
+          wxm = hx_2 * ((gx + i > 0) ? 1.f : 0.f);
+        }
+        float axp = wxp * ((p_r + pc) * 0.5f);
+        float axm = wxm * ((p_l + pc) * 0.5f);
+        eyp[i] = wyp * ((pD[i] + pc) * 0.5f);
+        eym[i] = wym * ((pU[i] + pc) * 0.5f);
+        const float sumH = ((axp + axm) + eyp[i]) + eym[i];
+        denU[i] = fmaf(J11[i], ksi[i], sumH);
+        denV[i] = fmaf(J22[i], ksi[i], sumH);
+        if (!inside[i]) {  // inert cell: stays at zero increment, on the fast division path
+          axp = axm = eyp[i] = eym[i] = 0.f;
+          denU[i] = denV[i] = 1.f;
+        }
+        // axm(x) == axp(x-1) bit for bit for x >= 1 (same products, commuted add): only the strip's
+        // first axm is kept separately
+        if (i == 0) t.ex[0] = axm;
+        t.ex[i + 1] = axp;
+        rU[i] = fast_path_rcp(denU[i]);
+        rV[i] = fast_path_rcp(denV[i]);
+        t.den_ok = t.den_ok && rU[i] != 0.f && rV[i] != 0.f;
+        t.su[i] = t.uc[i] + du[i];
+        t.sv[i] = t.vc[i] + t.dv[i];
+      }
+      st4(sm + P_EYP * PL + soff, eyp);
+      st4(sm + P_EYM * PL + soff, eym);
+      st4(sm + P_DENU * PL + soff, denU);
+      st4(sm + P_DENV * PL + soff, denV);
+      st4(sm + P_RU * PL + soff, rU);
+      st4(sm + P_RV * PL + soff, rV);
+      st4(sm + P_SU0 * PL + soff, t.su);
+      st4(sm + P_SV0 * PL + soff, t.sv);
     }
     __syncthreads();
 
-    // ---------------- phase D: Jacobi sweeps ----------------
+    // ---------------- phase D: Jacobi sweeps (solve_2d.cu:350-367 as compiled) ----------------
     for (int k = 1; k <= a.sweeps; ++k) {
-      const int grow = a.sweeps - k;
-      const int wx0 = max(0, ox0 - grow), wx1 = min(w, ox1 + grow);
-      const int wy0 = max(0, oy0 - grow), wy1 = min(h, oy1 + grow);
-      const float* cur_u = sm + ((k & 1) ? P_SU0 : P_SU1) * PL;
-      const float* cur_v = sm + ((k & 1) ? P_SV0 : P_SV1) * PL;
-      float* nxt_u = sm + ((k & 1) ? P_SU1 : P_SU0) * PL;
-      float* nxt_v = sm + ((k & 1) ? P_SV1 : P_SV0) * PL;
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const int y = gy[s];
-        const bool y_lo = (y == 0), y_hi = (y == h - 1);
-        const float suL = __shfl_up_sync(0xffffffffu, su[s][3], 1), suR = __shfl_down_sync(0xffffffffu, su[s][0], 1);
-        const float svL = __shfl_up_sync(0xffffffffu, sv[s][3], 1), svR = __shfl_down_sync(0xffffffffu, sv[s][0], 1);
-        const bool row_active = y >= wy0 && y < wy1;
-        float nu[4], nv[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { nu[i] = su[s][i]; nv[i] = sv[s][i]; }
-        if (row_active && gx + 3 >= wx0 && gx < wx1) {
-          float suU[4], suD[4], svU[4], svD[4], eyp[4], eym[4], denU[4], denV[4], nJ13v[4], nJ23v[4];
-          unpack(ld4(cur_u + soff[s] - LW), suU); unpack(ld4(cur_u + soff[s] + LW), suD);
-          unpack(ld4(cur_v + soff[s] - LW), svU); unpack(ld4(cur_v + soff[s] + LW), svD);
-          unpack(ld4(sm + P_EYP * PL + soff[s]), eyp); unpack(ld4(sm + P_EYM * PL + soff[s]), eym);
-          unpack(ld4(sm + P_DENU * PL + soff[s]), denU); unpack(ld4(sm + P_DENV * PL + soff[s]), denV);
-          unpack(ld4(sm + P_NJ13 * PL + soff[s]), nJ13v); unpack(ld4(sm + P_NJ23 * PL + soff[s]), nJ23v);
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int x = gx + i;
-            if (x >= wx0 && x < wx1) {
-              const bool x_lo = (x == 0), x_hi = (x == w - 1);
-              const float sul_raw = i > 0 ? su[s][i - 1] : suL, sur_raw = i < 3 ? su[s][i + 1] : suR;
-              const float svl_raw = i > 0 ? sv[s][i - 1] : svL, svr_raw = i < 3 ? sv[s][i + 1] : svR;
-              const float axm = ex[s][i], axp = ex[s][i + 1];
-              const float u0 = uc[s][i], v0 = vc[s][i];
-              // solve_2d.cu:350-367 as compiled (fma chain; (-J13) - J12*dv fused by ptxas)
-              float sumU = axm * (nb_lo(x_lo, sul_raw, sur_raw) - u0);
-              sumU = fmaf(axp, nb_hi(x_hi, sul_raw, sur_raw) - u0, sumU);
-              sumU = fmaf(eyp[i], nb_hi(y_hi, suU[i], suD[i]) - u0, sumU);
-              sumU = fmaf(eym[i], nb_lo(y_lo, suU[i], suD[i]) - u0, sumU);
-              float sumV = axm * (nb_lo(x_lo, svl_raw, svr_raw) - v0);
-              sumV = fmaf(axp, nb_hi(x_hi, svl_raw, svr_raw) - v0, sumV);
-              sumV = fmaf(eyp[i], nb_hi(y_hi, svU[i], svD[i]) - v0, sumV);
-              sumV = fmaf(eym[i], nb_lo(y_lo, svU[i], svD[i]) - v0, sumV);
-              const float kk = ksi[s][i];
-              const float r_du = fmaf(kk, fmaf(nJ12[s][i], dv[s][i], nJ13v[i]), sumU) / denU[i];
-              const float r_dv = fmaf(kk, fmaf(nJ12[s][i], r_du, nJ23v[i]), sumV) / denV[i];
-              du[s][i] = r_du;
-              dv[s][i] = r_dv;
-              nu[i] = u0 + r_du;
-              nv[i] = v0 + r_dv;
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) { su[s][i] = nu[i]; sv[s][i] = nv[i]; }
-        st4(nxt_u + soff[s], nu);
-        st4(nxt_v + soff[s], nv);
-      }
-      __syncthreads();
-    }
-  }
-
-  // ---------------- phase E: store du, dv of the output tile ----------------
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const int y = gy[s];
-    if (y < oy0 || y >= oy1) continue;
-    float* rdu = a.du_out + (size_t)y * pitch;
-    float* rdv = a.dv_out + (size_t)y * pitch;
-    if (gx >= ox0 && gx + 3 < ox1) {
-      st4(rdu + gx, du[s]);
-      st4(rdv + gx, dv[s]);
-    } else {
+      const float* cur_u = sm + ((k & 1) ? P_SU0 : P_SU1) * PL + soff;
+      const float* cur_v = sm + ((k & 1) ? P_SV0 : P_SV1) * PL + soff;
+      float* nxt_u = sm + ((k & 1) ? P_SU1 : P_SU0) * PL + soff;
+      float* nxt_v = sm + ((k & 1) ? P_SV1 : P_SV0) * PL + soff;
+      const float suL = __shfl_up_sync(0xffffffffu, t.su[3], 1), suR = __shfl_down_sync(0xffffffffu, t.su[0], 1);
+      const float svL = __shfl_up_sync(0xffffffffu, t.sv[3], 1), svR = __shfl_down_sync(0xffffffffu, t.sv[0], 1);
+      float nU[4], nD[4], eyp[4], eym[4], sumU[4], sumV[4];
+      unpack(ld4(sm + P_EYP * PL + soff), eyp);
+      unpack(ld4(sm + P_EYM * PL + soff), eym);
+      unpack(ld4(cur_u + up_off), nU);
+      unpack(ld4(cur_u + dn_off), nD);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const int x = gx + i;
-        if (x >= ox0 && x < ox1) { rdu[x] = du[s][i]; rdv[x] = dv[s][i]; }
+        float l, r;
+        x_nb<BORDER>(t.su, suL, suR, i, x_lo, i_hi, l, r);
+        const float u0 = t.uc[i];
+        // a mul, then an fma chain in the order xm, xp, yp, ym
+        float s = t.ex[i] * (l - u0);
+        s = fmaf(t.ex[i + 1], r - u0, s);
+        s = fmaf(eyp[i], nD[i] - u0, s);
+        sumU[i] = fmaf(eym[i], nU[i] - u0, s);
+      }
+      unpack(ld4(cur_v + up_off), nU);
+      unpack(ld4(cur_v + dn_off), nD);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float l, r;
+        x_nb<BORDER>(t.sv, svL, svR, i, x_lo, i_hi, l, r);
+        const float v0 = t.vc[i];
+        float s = t.ex[i] * (l - v0);
+        s = fmaf(t.ex[i + 1], r - v0, s);
+        s = fmaf(eyp[i], nD[i] - v0, s);
+        sumV[i] = fmaf(eym[i], nU[i] - v0, s);
+      }
+      // (-J13) - J12*dv is one FFMA in the reference SASS
+      float ksi[4], nJ12[4], nj[4], den[4], rcp[4], num[4], rdv[4];
+      unpack(ld4(sm + P_KSI * PL + soff), ksi);
+      unpack(ld4(sm + P_NJ12 * PL + soff), nJ12);
+      unpack(ld4(sm + P_NJ13 * PL + soff), nj);
+      unpack(ld4(sm + P_DENU * PL + soff), den);
+      unpack(ld4(sm + P_RU * PL + soff), rcp);
+#pragma unroll
+      for (int i = 0; i < 4; i++) num[i] = fmaf(ksi[i], fmaf(nJ12[i], t.dv[i], nj[i]), sumU[i]);
+      div_rn4(num, den, rcp, t.den_ok, du);
+      unpack(ld4(sm + P_NJ23 * PL + soff), nj);
+      unpack(ld4(sm + P_DENV * PL + soff), den);
+      unpack(ld4(sm + P_RV * PL + soff), rcp);
+#pragma unroll
+      for (int i = 0; i < 4; i++) num[i] = fmaf(ksi[i], fmaf(nJ12[i], du[i], nj[i]), sumV[i]);
+      div_rn4(num, den, rcp, t.den_ok, rdv);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        t.dv[i] = rdv[i];
+        t.su[i] = t.uc[i] + du[i];
+        t.sv[i] = t.vc[i] + rdv[i];
+      }
+      st4(nxt_u, t.su);
+      st4(nxt_v, t.sv);
+      __syncthreads();
+    }
+
+    // ---------------- phase E: store du, dv of the output tile ----------------
+    if (gy >= oy0 && gy < oy1) {
+      float* rdu = a.du_out + (size_t)gy * pitch;
+      float* rdvp = a.dv_out + (size_t)gy * pitch;
+      if (gx >= ox0 && gx + 3 < ox1) {
+        st4(rdu + gx, du);
+        st4(rdvp + gx, t.dv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int x = gx + i;
+          if (x >= ox0 && x < ox1) { rdu[x] = du[i]; rdvp[x] = t.dv[i]; }
+        }
       }
     }
   }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(NT, 1) solve_pass_kernel(const SolveArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  // does this CTA's region reach the image border (or beyond)?
+  const int lx0 = blockIdx.x * a.ow - a.halo_x, ly0 = blockIdx.y * a.oh - a.halo_y;
+  const bool border = lx0 <= 0 || lx0 + LW >= a.w || ly0 <= 0 || ly0 + LH >= a.h;
+  if (border) pass_body<GRAD, true>(a, sm);
+  else pass_body<GRAD, false>(a, sm);
 }
 
 cudaError_t solve_pass_configure() {
