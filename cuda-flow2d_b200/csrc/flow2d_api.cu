@@ -169,11 +169,26 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
     a.phi_out = want_phi ? phi : nullptr; a.ksi_out = want_phi ? ksi : nullptr;
     a.sweeps = inner; a.outer = outer;
     a.ow = kSolveLW; a.oh = kSolveLH; a.halo_x = 4; a.halo_y = 1;
-    launch_solve_pass(h->stream, a, grad, 1, 1);
+    launch_solve_pass(h->stream, a, grad, 1, 1, g.h + 2);  // image rows + one apron row above and below
     return check_launch(h, "solve_pass(resident)", 1);
   }
 
-  int S = p->sweeps_per_pass > 0 ? p->sweeps_per_pass : 5;
+  int S = p->sweeps_per_pass;
+  if (S <= 0) {
+    // Pick the sweeps per pass that minimises the modelled solve time.  Measured on B200 (ncu and
+    // bench.py, profiles/): per wave of CTAs a pass costs ~11 us of setup when it computes phi/ksi,
+    // ~7.5 us when it reloads them, plus ~0.85 us per sweep; region 64 x 48, halo S+1 rows and
+    // 4 (S <= 3) or 8 columns per side.
+    double best = 1e300;
+    for (int s = 1; s <= FLOW2D_MAX_SWEEPS_PER_PASS; ++s) {
+      const int np = (inner + s - 1) / s;
+      const int ow = kSolveLW - 2 * ((s + 1 <= 4) ? 4 : 8), oh = kSolveLH - 2 * (s + 1);
+      double waves = (double)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) / 148.0;
+      if (waves < 1.0) waves = 1.0;
+      const double cost = waves * (11.0 + (np - 1) * 7.5 + 0.85 * inner);
+      if (cost < best) { best = cost; S = s; }
+    }
+  }
   if (S > FLOW2D_MAX_SWEEPS_PER_PASS) S = FLOW2D_MAX_SWEEPS_PER_PASS;
   const int npass = (inner + S - 1) / S;
   const long long total = (long long)outer * npass;

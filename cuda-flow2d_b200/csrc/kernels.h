@@ -42,6 +42,7 @@ struct SolveArgs {
 
 size_t solve_pass_smem_bytes();
 cudaError_t solve_pass_configure();
-void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y);
+// rows > 0: launch only that many region rows (resident mode of a level with few rows)
+void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows = 0);
 
 }  // namespace flow2d

@@ -128,38 +128,51 @@ void launch_resample(cudaStream_t st, const float* const* in, float* const* tmp,
 // fma(w11,f11, fma(w01,f01, fma(f00,w00, w10*f10))).  Index work (floor, clamp, OOB/NaN test)
 // is bit exact by construction.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_pixel(const float* __restrict__ f0, const float* __restrict__ f1, float u, float v,
+                                            int xx, int yy, size_t c, int w, int h, int pitch, float rhx, float rhy,
+                                            float bx, float by) {
+  const float x_f = fmaf(rhx, u, (float)xx);
+  const float y_f = fmaf(rhy, v, (float)yy);
+  if ((x_f < 0.f) || (x_f > bx) || (y_f < 0.f) || (y_f > by) || isnan(x_f) || isnan(y_f)) return f0[c];
+  const int x = (int)floorf(x_f), y = (int)floorf(y_f);
+  const float dx = x_f - (float)x, dy = y_f - (float)y;
+  const int x1 = min(w - 1, x + 1), y1 = min(h - 1, y + 1);
+  const float ox = 1.f - dx, oy = 1.f - dy;
+  const float w00 = ox * oy, w10 = dx * oy, w01 = ox * dy, w11 = dx * dy;
+  const float* r0 = f1 + (size_t)y * pitch;
+  const float* r1 = f1 + (size_t)y1 * pitch;
+  float val = w10 * r0[x1];
+  val = fmaf(r0[x], w00, val);
+  val = fmaf(w01, r1[x], val);
+  return fmaf(w11, r1[x1], val);
+}
+
+// One thread = four consecutive pixels: float4 loads of u, v, one float4 store, 16 gathers in flight.
 __global__ void __launch_bounds__(256)
 warp_kernel(const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ u,
             const float* __restrict__ v, float* __restrict__ out, int w, int h, int pitch, float rhx, float rhy) {
-  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xx = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int yy = blockIdx.y * blockDim.y + threadIdx.y;
   if (xx >= w || yy >= h) return;
   const size_t c = (size_t)yy * pitch + xx;
-  const float x_f = fmaf(rhx, u[c], (float)xx);
-  const float y_f = fmaf(rhy, v[c], (float)yy);
   const float bx = (float)(w - 1), by = (float)(h - 1);
-  float val;
-  if ((x_f < 0.f) || (x_f > bx) || (y_f < 0.f) || (y_f > by) || isnan(x_f) || isnan(y_f)) {
-    val = f0[c];
+  if (xx + 3 < w) {
+    const float4 uu = *reinterpret_cast<const float4*>(u + c), vv = *reinterpret_cast<const float4*>(v + c);
+    float4 o;
+    o.x = warp_pixel(f0, f1, uu.x, vv.x, xx, yy, c, w, h, pitch, rhx, rhy, bx, by);
+    o.y = warp_pixel(f0, f1, uu.y, vv.y, xx + 1, yy, c + 1, w, h, pitch, rhx, rhy, bx, by);
+    o.z = warp_pixel(f0, f1, uu.z, vv.z, xx + 2, yy, c + 2, w, h, pitch, rhx, rhy, bx, by);
+    o.w = warp_pixel(f0, f1, uu.w, vv.w, xx + 3, yy, c + 3, w, h, pitch, rhx, rhy, bx, by);
+    *reinterpret_cast<float4*>(out + c) = o;
   } else {
-    const int x = (int)floorf(x_f), y = (int)floorf(y_f);
-    const float dx = x_f - (float)x, dy = y_f - (float)y;
-    const int x1 = min(w - 1, x + 1), y1 = min(h - 1, y + 1);
-    const float ox = 1.f - dx, oy = 1.f - dy;
-    const float w00 = ox * oy, w10 = dx * oy, w01 = ox * dy, w11 = dx * dy;
-    const float* r0 = f1 + (size_t)y * pitch;
-    const float* r1 = f1 + (size_t)y1 * pitch;
-    val = w10 * r0[x1];
-    val = fmaf(r0[x], w00, val);
-    val = fmaf(w01, r1[x], val);
-    val = fmaf(w11, r1[x1], val);
+    for (int i = 0; xx + i < w; i++)
+      out[c + i] = warp_pixel(f0, f1, u[c + i], v[c + i], xx + i, yy, c + i, w, h, pitch, rhx, rhy, bx, by);
   }
-  out[c] = val;
 }
 
 void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float* u, const float* v, float* out,
                  const LevelGeom& g) {
-  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
+  dim3 block(32, 8), grid((g.w + 127) / 128, (g.h + 7) / 8);
   warp_kernel<<<grid, block, 0, st>>>(f0, f1, u, v, out, g.w, g.h, g.pitch, 1.f / g.hx, 1.f / g.hy);
 }
 
@@ -173,17 +186,39 @@ void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float*
 __global__ void __launch_bounds__(256)
 derivatives_kernel(const float* __restrict__ f0, const float* __restrict__ f1, float* __restrict__ fx,
                    float* __restrict__ fy, float* __restrict__ ft, int w, int h, int pitch, float hx4, float hy4) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread = four consecutive pixels (float4 rows; the two x neighbours outside the strip are scalar loads)
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
-  const int xm = mirror_clamp(x - 1, w), xp = mirror_clamp(x + 1, w);
   const int ym = mirror_clamp(y - 1, h), yp = mirror_clamp(y + 1, h);
-  const size_t row = (size_t)y * pitch;
-  const size_t c = row + x;
-  fx[c] = (((f0[row + xp] - f0[row + xm]) + f1[row + xp]) - f1[row + xm]) / hx4;
-  fy[c] = (((f0[(size_t)yp * pitch + x] - f0[(size_t)ym * pitch + x]) + f1[(size_t)yp * pitch + x]) -
-           f1[(size_t)ym * pitch + x]) / hy4;
-  ft[c] = f1[c] - f0[c];
+  const size_t row = (size_t)y * pitch, up = (size_t)ym * pitch, dn = (size_t)yp * pitch;
+  if (x + 3 < w) {
+    const float4 a0 = *reinterpret_cast<const float4*>(f0 + row + x), a1 = *reinterpret_cast<const float4*>(f1 + row + x);
+    const float4 u0 = *reinterpret_cast<const float4*>(f0 + up + x), u1 = *reinterpret_cast<const float4*>(f1 + up + x);
+    const float4 d0 = *reinterpret_cast<const float4*>(f0 + dn + x), d1 = *reinterpret_cast<const float4*>(f1 + dn + x);
+    const int xl = mirror_clamp(x - 1, w), xr = mirror_clamp(x + 4, w);
+    const float l0 = f0[row + xl], l1 = f1[row + xl], r0 = f0[row + xr], r1 = f1[row + xr];
+    const float c0[6] = {l0, a0.x, a0.y, a0.z, a0.w, r0}, c1[6] = {l1, a1.x, a1.y, a1.z, a1.w, r1};
+    const float p0[4] = {u0.x, u0.y, u0.z, u0.w}, p1[4] = {u1.x, u1.y, u1.z, u1.w};
+    const float q0[4] = {d0.x, d0.y, d0.z, d0.w}, q1[4] = {d1.x, d1.y, d1.z, d1.w};
+    float ox[4], oy[4], ot[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      ox[i] = (((c0[i + 2] - c0[i]) + c1[i + 2]) - c1[i]) / hx4;
+      oy[i] = (((q0[i] - p0[i]) + q1[i]) - p1[i]) / hy4;
+      ot[i] = c1[i + 1] - c0[i + 1];
+    }
+    *reinterpret_cast<float4*>(fx + row + x) = make_float4(ox[0], ox[1], ox[2], ox[3]);
+    *reinterpret_cast<float4*>(fy + row + x) = make_float4(oy[0], oy[1], oy[2], oy[3]);
+    *reinterpret_cast<float4*>(ft + row + x) = make_float4(ot[0], ot[1], ot[2], ot[3]);
+  } else {
+    for (int i = 0; x + i < w; i++) {
+      const int xc = x + i, xm = mirror_clamp(xc - 1, w), xp = mirror_clamp(xc + 1, w);
+      fx[row + xc] = (((f0[row + xp] - f0[row + xm]) + f1[row + xp]) - f1[row + xm]) / hx4;
+      fy[row + xc] = (((f0[dn + xc] - f0[up + xc]) + f1[dn + xc]) - f1[up + xc]) / hy4;
+      ft[row + xc] = f1[row + xc] - f0[row + xc];
+    }
+  }
 }
 
 // Gradient-constancy motion tensor (solve_2d.cu:868-884) from the fx/fy/ft planes.  The reference
@@ -220,7 +255,7 @@ grad_tensor_kernel(const float* __restrict__ fx, const float* __restrict__ fy, c
 
 void launch_derivatives(cudaStream_t st, const float* f0, const float* f1w, float* fx, float* fy, float* ft,
                         const LevelGeom& g) {
-  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
+  dim3 block(32, 8), grid((g.w + 127) / 128, (g.h + 7) / 8);
   derivatives_kernel<<<grid, block, 0, st>>>(f0, f1w, fx, fy, ft, g.w, g.h, g.pitch, g.hx * 4.f, g.hy * 4.f);
 }
 

@@ -101,6 +101,9 @@ __device__ __forceinline__ float fast_path_rcp(float d) {  // 0 = "divisor not s
   const float r = fmaf(r0, e, r0);
   return in_fast_range(d) ? r : 0.f;
 }
+// The rare full division lives out of line: ~40 instructions per site would otherwise be inlined at
+// every one of the ~50 call sites and blow the instruction cache.
+__device__ __noinline__ float slow_div(float a, float d) { return a / d; }
 // Four quotients.  Common case (all dividends in range): 12 FMA-pipe instructions and one branch.
 __device__ __forceinline__ void div_rn4(const float (&a)[4], const float (&d)[4], const float (&r)[4], bool den_ok,
                                         float (&q)[4]) {
@@ -116,7 +119,7 @@ __device__ __forceinline__ void div_rn4(const float (&a)[4], const float (&d)[4]
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (a[i] == 0.f && r[i] != 0.f) q[i] = q0[i];
-      else if (!(r[i] != 0.f && in_fast_range(a[i]))) q[i] = a[i] / d[i];
+      else if (!(r[i] != 0.f && in_fast_range(a[i]))) q[i] = slow_div(a[i], d[i]);
     }
   }
 }
@@ -159,11 +162,12 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   const int gx = ox0 - a.halo_x + lx;  // multiple of 4
   const int gy = oy0 - a.halo_y + row;
   const int soff = row * LW + lx;
-  // Neighbour rows.  Image border: the mirrored neighbour is the opposite neighbour.  Rows 0 and
-  // LH-1 of the region have no neighbour row in shared memory (they are never exact anyway).
-  int up_off = row > 0 ? -LW : LW, dn_off = row < LH - 1 ? LW : -LW;
+  const int last_row = (int)(blockDim.x >> 4) - 1;  // LH-1, or fewer rows for a small resident level
+  // Neighbour rows.  Image border: the mirrored neighbour is the opposite neighbour.  The first and
+  // last row of the region have no neighbour row in shared memory (they are never exact anyway).
+  int up_off = row > 0 ? -LW : LW, dn_off = row < last_row ? LW : -LW;
   if (BORDER) {
-    if (gy == 0 && row < LH - 1) up_off = LW;
+    if (gy == 0 && row < last_row) up_off = LW;
     if (gy == h - 1 && row > 0) dn_off = -LW;
   }
   const bool x_lo = BORDER && gx == 0;        // only element 0 of a strip can be x == 0 (gx % 4 == 0)
@@ -396,6 +400,13 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
 
     // ---------------- phase D: Jacobi sweeps (solve_2d.cu:350-367 as compiled) ----------------
     for (int k = 1; k <= a.sweeps; ++k) {
+      // Rows further than sweeps-k from the output tile can no longer influence it: whole warps
+      // (two rows) outside that window skip the sweep (nothing reads what they would write).
+      const int grow = a.sweeps - k;
+      if (!__any_sync(0xffffffffu, gy >= oy0 - grow && gy < oy1 + grow)) {
+        __syncthreads();
+        continue;
+      }
       const float* cur_u = sm + ((k & 1) ? P_SU0 : P_SU1) * PL + soff;
       const float* cur_v = sm + ((k & 1) ? P_SV0 : P_SV1) * PL + soff;
       float* nxt_u = sm + ((k & 1) ? P_SU1 : P_SU0) * PL + soff;
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(NT, 1) solve_pass_kernel(const SolveArgs a) {
   extern __shared__ __align__(16) float sm[];
   // does this CTA's region reach the image border (or beyond)?
   const int lx0 = blockIdx.x * a.ow - a.halo_x, ly0 = blockIdx.y * a.oh - a.halo_y;
-  const bool border = lx0 <= 0 || lx0 + LW >= a.w || ly0 <= 0 || ly0 + LH >= a.h;
+  const bool border = lx0 <= 0 || lx0 + LW >= a.w || ly0 <= 0 || ly0 + (int)(blockDim.x >> 4) >= a.h;
   if (border) pass_body<GRAD, true>(a, sm);
   else pass_body<GRAD, false>(a, sm);
 }
@@ -493,8 +504,10 @@ cudaError_t solve_pass_configure() {
                               (int)solve_pass_smem_bytes());
 }
 
-void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y) {
-  dim3 grid(grid_x, grid_y), block(NT);
+void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows) {
+  // rows: region rows actually needed (resident mode of a small level); whole warps = pairs of rows
+  const int nrows = rows <= 0 || rows > LH ? LH : (rows + 1) / 2 * 2;
+  dim3 grid(grid_x, grid_y), block(nrows * (LW / 4));
   if (grad) solve_pass_kernel<true><<<grid, block, solve_pass_smem_bytes(), st>>>(a);
   else solve_pass_kernel<false><<<grid, block, solve_pass_smem_bytes(), st>>>(a);
 }

@@ -3,7 +3,8 @@
 //   cuda-flow2d                      settings.xml in the current directory
 //   cuda-flow2d <settings file>
 //   cuda-flow2d <file1> <file2> <width> <height> [<counter>] <output path> [<alpha> <sigma>]
-// Outputs: <out><counter>flow-u-W-H.raw, flow-v-W-H.raw (float32), amp-W-H.raw (float32 magnitude).
+// Outputs: <out><counter>flow-u-W-H.raw, flow-v-W-H.raw (float32), res.pgm (colour-coded flow, binary PPM),
+// amp-W-H.raw (float32 magnitude).
 // Exit codes: 0 ok / usage, 1 no CUDA device, 2 input files unreadable, 3 settings unreadable.
 // Differences: no getchar() at exit; the 8-bit reader is wired to Mode@imageType="8-bit";
 // files are also looked up under Input/Path@inputPath when they are not found in the CWD.
@@ -15,6 +16,7 @@
 #include <vector>
 
 #include "flow2d.h"
+#include "io_utils.h"
 #include "optical_flow_2d.h"
 #include "settings.h"
 
@@ -125,15 +127,8 @@ int main(int argc, char** argv) {
   const string suffix = "-" + std::to_string(width) + "-" + std::to_string(height) + ".raw";
   flow_u.WriteRAWToFileF32((output_path + counter + "flow-u" + suffix).c_str());
   flow_v.WriteRAWToFileF32((output_path + counter + "flow-v" + suffix).c_str());
-  {  // amp-W-H.raw: flow magnitude (src/utils/io_utils.cpp:68-90)
-    Data2D amp(width, height);
-    for (size_t y = 0; y < height; ++y)
-      for (size_t x = 0; x < width; ++x) {
-        const float a = flow_u.Data(x, y), b = flow_v.Data(x, y);
-        amp.Data(x, y) = std::sqrt(a * a + b * b);
-      }
-    amp.WriteRAWToFileF32((output_path + counter + "amp" + suffix).c_str());
-  }
+  IOUtils::WriteFlowToImageRGB(flow_u, flow_v, 10, output_path + counter + "res.pgm");  // src/main.cpp:212
+  IOUtils::WriteMagnitudeToFileF32(flow_u, flow_v, output_path + counter + "amp" + suffix);
   optical_flow.Destroy();
   return 0;
 }

@@ -1,0 +1,68 @@
+"""The cuda-flow2d command line (cuda-flow2d_b200/bin/cuda-flow2d) against the reference's own
+executable (oracle/_ref/cuda-flow2d, its unmodified main.cpp) on the bundled rub pair: same argv
+form, and byte-identical flow-u / flow-v / amp / res.pgm files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REF_DIR, ROOT
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "cuda-flow2d_b200", "bin", "cuda-flow2d")
+REF_CLI = os.path.join(REF_DIR, "cuda-flow2d")
+
+
+def _run(exe, args, cwd):
+    return subprocess.run([exe] + [str(a) for a in args], cwd=cwd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, timeout=600)
+
+
+def test_argv_form_matches_reference_files(rub, tmp_path):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/cuda-flow2d is not present")
+    f0, f1 = rub
+    (tmp_path / "ours").mkdir()
+    (tmp_path / "ref").mkdir()
+    f0.tofile(tmp_path / "rub1_f32.raw")
+    f1.tofile(tmp_path / "rub2_f32.raw")
+    # cuda-flow2d <file1> <file2> <W> <H> <counter> <output path>   (src/main.cpp:107-118, defaults 70-80)
+    r = _run(CLI, ["rub1_f32.raw", "rub2_f32.raw", 584, 388, "t_", "ours/"], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    assert b"Total GPU computation time" in r.stdout
+    q = _run(REF_CLI, ["rub1_f32.raw", "rub2_f32.raw", 584, 388, "t_", "ref/"], tmp_path)
+    assert q.returncode == 0, q.stdout.decode()[-2000:]
+    for name in ("t_flow-u-584-388.raw", "t_flow-v-584-388.raw", "t_amp-584-388.raw", "t_res.pgm"):
+        a = (tmp_path / "ours" / name).read_bytes()
+        b = (tmp_path / "ref" / name).read_bytes()
+        assert len(a) == len(b) and a == b, "%s differs (%d vs %d bytes)" % (name, len(a), len(b))
+
+
+def test_settings_form_8bit_and_exit_codes(rub, oracle, tmp_path):
+    f0, f1 = rub
+    f0.astype(np.uint8).tofile(tmp_path / "rub1.raw")  # the bundled files are 8-bit
+    f1.astype(np.uint8).tofile(tmp_path / "rub2.raw")
+    (tmp_path / "out").mkdir()
+    xml = """<?xml version="1.0"?>
+<!-- settings.xml schema of the reference -->
+<OpticalFlow>
+  <Input><Path inputPath="%s/"/><Mode Nx="584" Ny="388" imageType="8-bit"><Files file1 ="rub1.raw" file2 ="rub2.raw"/></Mode></Input>
+  <Parameters><Method mode ="2d" run="flow" key="0" />
+    <Solver><Iterations inner="5" outer="20"/><Warping levels="20" scaling="0.9" medianRadius="5"/>
+      <Model sigma="0.45" alpha ="3.5" e_smooth="0.001" e_data="0.001"/></Solver></Parameters>
+  <Output><Path outputPath="out/"/></Output>
+</OpticalFlow>""" % tmp_path
+    (tmp_path / "settings.xml").write_text(xml)
+    r = _run(CLI, [], tmp_path)  # no argument: settings.xml in the current directory
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    u = np.fromfile(tmp_path / "out" / "flow-u-584-388.raw", np.float32).reshape(388, 584)
+    v = np.fromfile(tmp_path / "out" / "flow-v-584-388.raw", np.float32).reshape(388, 584)
+    ou, ov = oracle.compute_flow(f0, f1, oracle.make_params(levels=20, outer=20, alpha=3.5, sigma=0.45))
+    assert np.all(u == ou) and np.all(v == ov)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rub_c1a_reference.npz"))
+    assert np.all(u == z["u"]) and np.all(v == z["v"])  # = the reference build's flow for these settings
+    # exit codes of src/main.cpp: 3 = settings unreadable, 2 = input unreadable, 0 = usage
+    assert _run(CLI, ["missing.xml"], tmp_path).returncode == 3
+    assert _run(CLI, ["nope1.raw", "nope2.raw", 584, 388, "x_", "out/"], tmp_path).returncode == 2
+    assert _run(CLI, ["a", "b", "c"], tmp_path).returncode == 0
