@@ -70,6 +70,8 @@ def lib():
         L.flow2d_get_stream.argtypes = [vp]
         L.flow2d_compute.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params)]
         L.flow2d_compute_device.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params)]
+        L.flow2d_compute_async.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params)]
+        L.flow2d_synchronize.argtypes = [vp]
         L.flow2d_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_int), fp]
         L.flow2d_max_warp_level.restype = sz
         L.flow2d_max_warp_level.argtypes = [sz, sz, C.c_float]
@@ -81,6 +83,7 @@ def lib():
         L.flow2d_stage_add.argtypes = [vp, vp, vp, sz, sz]
         L.flow2d_stage_median.argtypes = [vp, vp, vp, sz, sz, sz]
         L.flow2d_stage_add_median.argtypes = [vp, vp, vp, vp, sz, sz, sz]
+        L.flow2d_debug_timing.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -193,8 +196,21 @@ class Flow2D:
         self._check(lib().flow2d_compute(self._h, host_ptr(f0), host_ptr(f1), host_ptr(out_u), host_ptr(out_v), C.byref(params)))
         return out_u, out_v
 
+    def compute_async(self, f0, f1, params, out_u, out_v):
+        """flow2d_compute_async: pinned torch CPU tensors in/out; returns at once, finish with synchronize()."""
+        for x in (f0, f1, out_u, out_v):
+            assert not x.is_cuda and x.is_pinned() and x.is_contiguous() and tuple(x.shape) == (self.height, self.width)
+        self._check(lib().flow2d_compute_async(self._h, C.c_void_p(f0.data_ptr()), C.c_void_p(f1.data_ptr()),
+                                               C.c_void_p(out_u.data_ptr()), C.c_void_p(out_v.data_ptr()), C.byref(params)))
+
+    def synchronize(self):
+        self._check(lib().flow2d_synchronize(self._h))
+
     def compute_device(self, d_f0, d_f1, d_u, d_v, params):
         self._check(lib().flow2d_compute_device(self._h, _ptr(d_f0), _ptr(d_f1), _ptr(d_u), _ptr(d_v), C.byref(params)))
+
+    def debug_timing(self, d_stamps):
+        self._check(lib().flow2d_debug_timing(self._h, _ptr(d_stamps)))
 
     # -- per-stage API on containers --
     def stage_blur(self, d_in, d_out, w, h, sigma):

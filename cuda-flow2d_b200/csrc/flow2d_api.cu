@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -48,6 +49,11 @@ struct flow2d_handle {
   long long launches = 0;
   int levels_run = 0;
   float device_ms = 0.f;
+  unsigned long long* timing = nullptr;  // debug: phase stamps of solve_pass (flow2d_debug_timing)
+  cudaGraphExec_t graph_exec = nullptr;  // captured level schedule of the last (buffers, parameters) combination
+  unsigned char graph_key[128] = {};
+  long long graph_launches = 0;
+  int graph_levels = 0;
   std::string err;
 };
 
@@ -159,6 +165,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   a.w = g.w; a.h = g.h; a.pitch = g.pitch;
   a.hx = g.hx; a.hy = g.hy;
   a.alpha = p->equation_alpha; a.e_smooth = p->equation_smoothness; a.e_data = p->equation_data;
+  a.timing = h->timing;
 
   // resident mode: the whole level (plus a one-cell apron) fits one CTA's region
   const bool fits = g.w + 4 + 1 <= kSolveLW && g.h + 1 + 1 <= kSolveLH;
@@ -194,6 +201,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   const long long total = (long long)outer * npass;
   float* bufs[2][2] = {{du_a, dv_a}, {du_b, dv_b}};
   long long pass = 0;
+  static const bool no_pdl = std::getenv("FLOW2D_NO_PDL") != nullptr;  // A/B switch for measurements
   const float *cur_du = nullptr, *cur_dv = nullptr;
   a.outer = 1;
   for (int o = 0; o < outer; ++o) {
@@ -213,6 +221,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       a.halo_x = (s + 1 <= 4) ? 4 : 8;
       a.ow = kSolveLW - 2 * a.halo_x;
       a.oh = kSolveLH - 2 * a.halo_y;
+      a.pdl = (pass > 0 && !no_pdl) ? 1 : 0;  // the first pass follows the derivatives kernel: plain launch
       launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (g.h + a.oh - 1) / a.oh);
       TRY(check_launch(h, "solve_pass", 1));
       cur_du = a.du_out; cur_dv = a.dv_out;
@@ -248,8 +257,8 @@ int validate_params(flow2d_handle* h, const flow2d_params* p, int* median) {
 }
 
 // The pyramid.  frame_0 / frame_1 / out_u / out_v are device containers.
-int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame_1, float* out_u, float* out_v,
-                      const flow2d_params* p) {
+int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1, float* out_u, float* out_v,
+                    const flow2d_params* p) {
   int median = 1;
   TRY(validate_params(h, p, &median));
   const size_t W = h->W, H = h->H;
@@ -319,6 +328,77 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
     --level;
     ++h->levels_run;
   }
+  return FLOW2D_OK;
+}
+
+// The level schedule of one (frames, flow, parameters) combination is captured into a CUDA graph
+// the first time and replayed afterwards: a sequence of frame pairs through one handle costs one
+// graph launch per pair instead of ~1 500 kernel launches of host work.
+struct GraphKey {
+  const void* ptr[4];
+  flow2d_params p;
+  const void* timing;
+};
+
+int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame_1, float* out_u, float* out_v,
+                      const flow2d_params* p) {
+  int median = 1;
+  TRY(validate_params(h, p, &median));
+  if (p->gaussian_sigma > 0.0f) {
+    GaussTaps taps;
+    TRY(gauss_taps(h, p->gaussian_sigma, &taps));
+  }
+  static const bool no_graph = std::getenv("FLOW2D_NO_GRAPH") != nullptr;  // A/B switch for measurements
+  if (no_graph) return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+
+  GraphKey key;
+  std::memset(&key, 0, sizeof key);
+  key.ptr[0] = frame_0; key.ptr[1] = frame_1; key.ptr[2] = out_u; key.ptr[3] = out_v;
+  // field by field: padding bytes of the caller's struct must not take part in the comparison
+  key.p.warp_levels_count = p->warp_levels_count; key.p.warp_scale_factor = p->warp_scale_factor;
+  key.p.outer_iterations_count = p->outer_iterations_count; key.p.inner_iterations_count = p->inner_iterations_count;
+  key.p.equation_alpha = p->equation_alpha; key.p.equation_smoothness = p->equation_smoothness;
+  key.p.equation_data = p->equation_data; key.p.median_radius = p->median_radius;
+  key.p.gaussian_sigma = p->gaussian_sigma; key.p.sweeps_per_pass = p->sweeps_per_pass;
+  key.p.resident_levels = p->resident_levels;
+  key.timing = h->timing;
+  if (h->graph_exec && std::memcmp(&key, h->graph_key, sizeof key) == 0) {
+    CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches = h->graph_launches;
+    h->levels_run = h->graph_levels;
+    return FLOW2D_OK;
+  }
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);  // e.g. the stream is already capturing
+  }
+  h->launches = 0;
+  const int rc = enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (rc != FLOW2D_OK || e != cudaSuccess || !graph) {
+    (void)cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != FLOW2D_OK) return rc;
+    return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaGraphDestroy(graph);
+    return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+  }
+  cudaGraphDestroy(graph);
+  h->graph_exec = exec;
+  static_assert(sizeof(GraphKey) <= sizeof(h->graph_key), "graph key storage too small");
+  std::memcpy(h->graph_key, &key, sizeof key);
+  h->graph_launches = h->launches;
+  h->graph_levels = h->levels_run;
+  CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
   return FLOW2D_OK;
 }
 
@@ -432,6 +512,7 @@ int flow2d_destroy(flow2d_handle* h) {
   if (!h) return FLOW2D_OK;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -471,8 +552,8 @@ int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, const float*
   return compute_on_device(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p);
 }
 
-int flow2d_compute(flow2d_handle* h, const float* frame_0, const float* frame_1, float* flow_u, float* flow_v,
-                   const flow2d_params* p) {
+int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* frame_1, float* flow_u, float* flow_v,
+                         const flow2d_params* p) {
   if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
   if (!frame_0 || !frame_1 || !flow_u || !flow_v) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null image pointer");
   CU_TRY(h, cudaSetDevice(h->device));
@@ -494,8 +575,31 @@ int flow2d_compute(flow2d_handle* h, const float* frame_0, const float* frame_1,
   CU_TRY(h, cudaMemcpy2DAsync(flow_u, row, out_u, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaMemcpy2DAsync(flow_v, row, out_v, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaEventRecord(h->ev_stop, st));
-  CU_TRY(h, cudaStreamSynchronize(st));
-  CU_TRY(h, cudaEventElapsedTime(&h->device_ms, h->ev_start, h->ev_stop));
+  return FLOW2D_OK;
+}
+
+int flow2d_synchronize(flow2d_handle* h) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (cudaEventQuery(h->ev_stop) == cudaSuccess && cudaEventQuery(h->ev_start) == cudaSuccess)
+    (void)cudaEventElapsedTime(&h->device_ms, h->ev_start, h->ev_stop);
+  (void)cudaGetLastError();
+  return FLOW2D_OK;
+}
+
+int flow2d_compute(flow2d_handle* h, const float* frame_0, const float* frame_1, float* flow_u, float* flow_v,
+                   const flow2d_params* p) {
+  int rc = flow2d_compute_async(h, frame_0, frame_1, flow_u, flow_v, p);
+  if (rc != FLOW2D_OK) return rc;
+  return flow2d_synchronize(h);
+}
+
+// Debug aid (not part of the drop-in surface): solve_pass writes 8 globaltimer stamps per CTA of the
+// LAST launch into this device buffer (null switches it off).
+int flow2d_debug_timing(flow2d_handle* h, unsigned long long* d_stamps) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  h->timing = d_stamps;
   return FLOW2D_OK;
 }
 

@@ -150,9 +150,18 @@ __device__ __forceinline__ void x_nb(const float (&c)[4], float L, float R, int 
   }
 }
 
+__device__ __forceinline__ void stamp(const SolveArgs& a, int slot) {
+  if (a.timing && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.timing[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+  }
+}
+
 template <bool GRAD, bool BORDER>
 __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   const int tid = threadIdx.x;
+  stamp(a, 0);
   const int row = tid >> 4;       // row of the region
   const int lx = 4 * (tid & 15);  // first column of the strip within the region
   const int w = a.w, h = a.h, pitch = a.pitch;
@@ -188,8 +197,17 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
 
   Strip t;
   float du[4];  // increment in u: live in phases A-C and as the sweeps' result, not across the sweeps
+  float fx[4], fy[4], ft[4];
+  // Programmatic dependent launch: this grid may have been started while the previous pass was still
+  // draining.  Everything the previous pass does not write (u, v, the derivative planes) is loaded
+  // first; du, dv, phi, ksi only after griddepcontrol.wait (= previous grid complete and flushed).
+  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;");
   load_strip(a.u, sa, t.uc);
   load_strip(a.v, sa, t.vc);
+  load_strip(a.fx, sa, fx);
+  load_strip(a.fy, sa, fy);
+  load_strip(a.ft, sa, ft);
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (a.du_in) {
     load_strip(a.du_in, sa, du);
     load_strip(a.dv_in, sa, t.dv);
@@ -210,10 +228,12 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
     // ------ phase A: remaining loads; motion tensor (solve_2d.cu:324-329 / 879-884); ksi (176-196) ------
     float phi[4];
     {
-      float fx[4], fy[4], ft[4], ksi[4];
-      load_strip(a.fx, sa, fx);
-      load_strip(a.fy, sa, fy);
-      load_strip(a.ft, sa, ft);
+      float ksi[4];
+      if (outer > 0) {
+        load_strip(a.fx, sa, fx);
+        load_strip(a.fy, sa, fy);
+        load_strip(a.ft, sa, ft);
+      }
       if (a.phi_in) {
         load_strip(a.phi_in, sa, phi);
         load_strip(a.ksi_in, sa, ksi);
@@ -262,6 +282,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
       st4(sm + P_NJ23 * PL + soff, J23);
     }
 
+    stamp(a, 1);
     if (!a.phi_in) {
       // ---------------- phase B: phi (solve_2d.cu:141-162) ----------------
       st4(sm + P_U * PL + soff, t.uc);
@@ -328,6 +349,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
     }
     st4(sm + P_PHI * PL + soff, phi);
     __syncthreads();  // phi published; every reader of P_U..P_DV is done, so their aliases are free
+    stamp(a, 2);
 
     // ---------------- phase C: weights and denominators (solve_2d.cu:333-349, 363, 367) ----------------
     {
@@ -397,6 +419,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
       st4(sm + P_SV0 * PL + soff, t.sv);
     }
     __syncthreads();
+    stamp(a, 3);
 
     // ---------------- phase D: Jacobi sweeps (solve_2d.cu:350-367 as compiled) ----------------
     for (int k = 1; k <= a.sweeps; ++k) {
@@ -468,6 +491,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
       __syncthreads();
     }
 
+    stamp(a, 4);
     // ---------------- phase E: store du, dv of the output tile ----------------
     if (gy >= oy0 && gy < oy1) {
       float* rdu = a.du_out + (size_t)gy * pitch;
@@ -483,6 +507,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         }
       }
     }
+    stamp(a, 5);
   }
 }
 
@@ -507,9 +532,18 @@ cudaError_t solve_pass_configure() {
 void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows) {
   // rows: region rows actually needed (resident mode of a small level); whole warps = pairs of rows
   const int nrows = rows <= 0 || rows > LH ? LH : (rows + 1) / 2 * 2;
-  dim3 grid(grid_x, grid_y), block(nrows * (LW / 4));
-  if (grad) solve_pass_kernel<true><<<grid, block, solve_pass_smem_bytes(), st>>>(a);
-  else solve_pass_kernel<false><<<grid, block, solve_pass_smem_bytes(), st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid_x, grid_y);
+  cfg.blockDim = dim3(nrows * (LW / 4));
+  cfg.dynamicSmemBytes = solve_pass_smem_bytes();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = a.pdl ? 1 : 0;  // only between consecutive passes of one solve (see SolveArgs::pdl)
+  if (grad) cudaLaunchKernelEx(&cfg, solve_pass_kernel<true>, a);
+  else cudaLaunchKernelEx(&cfg, solve_pass_kernel<false>, a);
 }
 
 }  // namespace flow2d

@@ -98,6 +98,13 @@ FLOW2D_API int flow2d_compute(flow2d_handle* h, const float* frame_0, const floa
 FLOW2D_API int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
                           float* d_flow_u, float* d_flow_v, const flow2d_params* p);
 
+/* Asynchronous form of flow2d_compute for pipelines that keep several handles busy at once (one
+ * stream each): enqueues H2D, the solve and D2H on the handle's stream and returns.  The host
+ * buffers must be page-locked (flow2d_host_alloc) and stay untouched until flow2d_synchronize(). */
+FLOW2D_API int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* frame_1,
+                         float* flow_u, float* flow_v, const flow2d_params* p);
+FLOW2D_API int flow2d_synchronize(flow2d_handle* h);
+
 /* Diagnostics of the last flow2d_compute*(): kernels launched, pyramid levels run, and (after
  * flow2d_compute only) the device time in ms between the first H2D and the last D2H -- the span
  * of the reference's "Total GPU computation time" (optical_flow_2d.cpp:179,548-554). */
@@ -144,6 +151,11 @@ FLOW2D_API int flow2d_stage_median(flow2d_handle* h, const float* d_in, float* d
 /* Fused 2 x add + 2 x median of one level (optical_flow_2d.cpp:409-449): out = median(a + b). */
 FLOW2D_API int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b, float* d_out,
                             size_t w, size_t h_, size_t radius);
+
+/* Debug aid, not part of the drop-in surface: every solve_pass CTA writes 8 %globaltimer stamps
+ * (entry, loads+tensor, phi, weights, sweeps, stores) into d_stamps (device memory, >= 8 * CTAs of the
+ * largest launch); NULL switches it off. */
+FLOW2D_API int flow2d_debug_timing(flow2d_handle* h, unsigned long long* d_stamps);
 
 /* Page-locked host memory for frames / flow fields, so the H2D / D2H copies of flow2d_compute are
  * plain DMA (the reference's optional ALLOCATE_PINNED_MEMORY path, src/data_types/data2d.cpp:52-60).
