@@ -84,6 +84,8 @@ def lib():
         L.flow2d_stage_median.argtypes = [vp, vp, vp, sz, sz, sz]
         L.flow2d_stage_add_median.argtypes = [vp, vp, vp, vp, sz, sz, sz]
         L.flow2d_debug_timing.argtypes = [vp, vp]
+        L.flow2d_compute_slab_device.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params), vp]
+        L.flow2d_stage_solve_slab.argtypes = [vp] * 7 + [sz, sz, C.c_float, C.c_float, C.POINTER(Params), vp]
         _LIB = L
     return _LIB
 
@@ -208,6 +210,15 @@ class Flow2D:
 
     def compute_device(self, d_f0, d_f1, d_u, d_v, params):
         self._check(lib().flow2d_compute_device(self._h, _ptr(d_f0), _ptr(d_f1), _ptr(d_u), _ptr(d_v), C.byref(params)))
+
+    def compute_slab_device(self, d_f0, d_f1, d_u, d_v, params, slab):
+        """flow2d_compute_slab_device; `slab` is a cuda_flow2d_b200.slab.Slab (keep its transport object alive)."""
+        self._check(lib().flow2d_compute_slab_device(self._h, _ptr(d_f0), _ptr(d_f1), _ptr(d_u), _ptr(d_v), C.byref(params),
+                                                     C.cast(C.pointer(slab), C.c_void_p)))
+
+    def stage_solve_slab(self, d_f0, d_f1w, d_u, d_v, d_du, d_dv, w, h, hx, hy, params, slab):
+        self._check(lib().flow2d_stage_solve_slab(self._h, _ptr(d_f0), _ptr(d_f1w), _ptr(d_u), _ptr(d_v), _ptr(d_du), _ptr(d_dv),
+                                                  w, h, hx, hy, C.byref(params), C.cast(C.pointer(slab), C.c_void_p)))
 
     def debug_timing(self, d_stamps):
         self._check(lib().flow2d_debug_timing(self._h, _ptr(d_stamps)))

@@ -148,7 +148,8 @@ LevelGeom geom(const flow2d_handle* h, size_t w, size_t hh, float hx, float hy) 
 // The result is left in du_a/dv_a; du_b/dv_b are scratch.  fx,fy,ft (and J in gradient mode) must
 // hold the derivative planes of this level.
 int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float* v, float* du_a, float* dv_a,
-              float* du_b, float* dv_b, float* phi, float* ksi, bool want_phi, const flow2d_params* p) {
+              float* du_b, float* dv_b, float* phi, float* ksi, bool want_phi, const flow2d_params* p,
+              const flow2d_slab* slab = nullptr) {
   const int outer = (int)p->outer_iterations_count, inner = (int)p->inner_iterations_count;
   if (outer == 0 || inner == 0) {
     // no sweep runs: the increment stays at its initial zero (cuda_operation_solve_2d.cpp:229-232)
@@ -166,6 +167,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   a.hx = g.hx; a.hy = g.hy;
   a.alpha = p->equation_alpha; a.e_smooth = p->equation_smoothness; a.e_data = p->equation_data;
   a.timing = h->timing;
+  a.y0 = 0; a.y1 = g.h;
 
   // resident mode: the whole level (plus a one-cell apron) fits one CTA's region
   const bool fits = g.w + 4 + 1 <= kSolveLW && g.h + 1 + 1 <= kSolveLH;
@@ -202,9 +204,53 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   float* bufs[2][2] = {{du_a, dv_a}, {du_b, dv_b}};
   long long pass = 0;
   static const bool no_pdl = std::getenv("FLOW2D_NO_PDL") != nullptr;  // A/B switch for measurements
-  const float *cur_du = nullptr, *cur_dv = nullptr;
+  float *cur_du = nullptr, *cur_dv = nullptr;
   a.outer = 1;
+
+  // Row-slab decomposition (flow2d.h): this rank produces rows [Y0, Y1) of the level.  A pass can
+  // only be exact where its input increment was exact S+1 rows further out, so the rows a rank
+  // works on shrink by S+1 per pass from both cut edges (never at the true image border) until the
+  // ghost rows are refreshed from the neighbours.  Exchanges happen between outer iterations only
+  // (phi / ksi of a multi-pass outer iteration are not exchanged).
+  int Y0 = 0, Y1 = g.h, ghost = 0;
+  bool slabbed = false;
+  if (slab && slab->world > 1) {
+    const int per_outer = npass * (S + 1);                   // rows lost per outer iteration
+    const int outers_per_exchange = 4;
+    ghost = per_outer * outers_per_exchange;
+    const size_t min_rows = slab->min_rows_per_rank ? slab->min_rows_per_rank : 128;
+    const int base = g.h / slab->world, extra = g.h % slab->world;
+    if ((size_t)base >= min_rows && base >= 2 * ghost) {
+      slabbed = true;
+      Y0 = slab->rank * base + (slab->rank < extra ? slab->rank : extra);
+      Y1 = Y0 + base + (slab->rank < extra ? 1 : 0);
+    }
+  }
+  int va = 0, vb = g.h;  // rows on which the current increment is exact on this rank
+  if (slabbed) {
+    va = Y0 - ghost > 0 ? Y0 - ghost : 0;
+    vb = Y1 + ghost < g.h ? Y1 + ghost : g.h;
+  }
+  bool after_exchange = false;
   for (int o = 0; o < outer; ++o) {
+    if (slabbed && o > 0) {
+      // would this outer iteration still cover the rank's own rows?
+      int sa = va, sb = vb, left = inner;
+      for (int q = 0; q < npass; ++q) {
+        const int s = (left + (npass - q) - 1) / (npass - q);
+        left -= s;
+        if (sa > 0) sa += s + 1;
+        if (sb < g.h) sb -= s + 1;
+      }
+      if (sa > Y0 || sb < Y1) {
+        if (slab->exchange(slab->user, 0, cur_du, cur_dv, h->pitch, (size_t)g.w, (size_t)g.h, (size_t)Y0, (size_t)Y1,
+                           (size_t)ghost) != 0)
+          return fail(h, FLOW2D_ERR_CUDA, "slab halo exchange failed");
+        va = Y0 - ghost > 0 ? Y0 - ghost : 0;
+        vb = Y1 + ghost < g.h ? Y1 + ghost : g.h;
+        after_exchange = true;
+      }
+    }
     int left = inner;
     for (int q = 0; q < npass; ++q, ++pass) {
       const int s = (left + (npass - q) - 1) / (npass - q);  // spread the sweeps evenly over the passes
@@ -221,11 +267,21 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       a.halo_x = (s + 1 <= 4) ? 4 : 8;
       a.ow = kSolveLW - 2 * a.halo_x;
       a.oh = kSolveLH - 2 * a.halo_y;
-      a.pdl = (pass > 0 && !no_pdl) ? 1 : 0;  // the first pass follows the derivatives kernel: plain launch
-      launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (g.h + a.oh - 1) / a.oh);
+      if (slabbed && pass > 0) {  // the very first pass starts from du = dv = 0, exact everywhere
+        if (va > 0) va += s + 1;
+        if (vb < g.h) vb -= s + 1;
+      }
+      a.y0 = va; a.y1 = vb;
+      a.pdl = (pass > 0 && !no_pdl && !after_exchange) ? 1 : 0;  // the first pass follows the derivatives kernel
+      after_exchange = false;
+      launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
       TRY(check_launch(h, "solve_pass", 1));
       cur_du = a.du_out; cur_dv = a.dv_out;
     }
+  }
+  if (slabbed) {
+    if (slab->exchange(slab->user, 1, du_a, dv_a, h->pitch, (size_t)g.w, (size_t)g.h, (size_t)Y0, (size_t)Y1, 0) != 0)
+      return fail(h, FLOW2D_ERR_CUDA, "slab gather failed");
   }
   return FLOW2D_OK;
 }
@@ -258,7 +314,7 @@ int validate_params(flow2d_handle* h, const flow2d_params* p, int* median) {
 
 // The pyramid.  frame_0 / frame_1 / out_u / out_v are device containers.
 int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1, float* out_u, float* out_v,
-                    const flow2d_params* p) {
+                    const flow2d_params* p, const flow2d_slab* slab = nullptr) {
   int median = 1;
   TRY(validate_params(h, p, &median));
   const size_t W = h->W, H = h->H;
@@ -314,7 +370,7 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     TRY(check_launch(h, "warp", 1));
     TRY(run_derivatives(h, g, fr[0], h->c[C_WARPED]));
     // solve (366-406)
-    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], false, p));
+    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], false, p, slab));
     // u += du, v += dv, median (409-449); the finest level writes the caller's flow containers
     {
       const float* a[2] = {u, v};
@@ -407,6 +463,10 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
 // ================================================================================================
 // C ABI
 // ================================================================================================
+#define STAGE_PROLOGUE(h)                                    \
+  if (!(h)) return FLOW2D_ERR_INVALID_ARGUMENT;              \
+  CU_TRY((h), cudaSetDevice((h)->device))
+
 extern "C" {
 
 const char* flow2d_version(void) { return "flow2d-b200 0.1.0 sm_100a"; }
@@ -595,6 +655,34 @@ int flow2d_compute(flow2d_handle* h, const float* frame_0, const float* frame_1,
   return flow2d_synchronize(h);
 }
 
+int flow2d_compute_slab_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, float* d_flow_u,
+                               float* d_flow_v, const flow2d_params* p, const flow2d_slab* slab) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null image pointer");
+  if (!slab || slab->world < 1 || slab->rank < 0 || slab->rank >= slab->world || (slab->world > 1 && !slab->exchange))
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "bad slab description");
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->launches = 0;
+  return enqueue_pyramid(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p, slab);  // callbacks inside: no graph capture
+}
+
+int flow2d_stage_solve_slab(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, const float* d_flow_u,
+                            const float* d_flow_v, float* d_flow_du, float* d_flow_dv, size_t w, size_t hh, float hx,
+                            float hy, const flow2d_params* p, const flow2d_slab* slab) {
+  STAGE_PROLOGUE(h);
+  if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v || !d_flow_du || !d_flow_dv || !p || !slab)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "solve: null argument");
+  if (slab->world < 1 || slab->rank < 0 || slab->rank >= slab->world || (slab->world > 1 && !slab->exchange))
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "bad slab description");
+  if (p->sweeps_per_pass < 0 || p->sweeps_per_pass > FLOW2D_MAX_SWEEPS_PER_PASS)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "sweeps_per_pass must be 0..%d", FLOW2D_MAX_SWEEPS_PER_PASS);
+  TRY(check_level(h, w, hh));
+  const LevelGeom g = geom(h, w, hh, hx, hy);
+  TRY(run_derivatives(h, g, d_frame_0, d_frame_1));
+  return run_solve(h, g, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI],
+                   false, p, slab);
+}
+
 // Debug aid (not part of the drop-in surface): solve_pass writes 8 globaltimer stamps per CTA of the
 // LAST launch into this device buffer (null switches it off).
 int flow2d_debug_timing(flow2d_handle* h, unsigned long long* d_stamps) {
@@ -604,9 +692,6 @@ int flow2d_debug_timing(flow2d_handle* h, unsigned long long* d_stamps) {
 }
 
 // ---- per-stage API ----
-#define STAGE_PROLOGUE(h)                                    \
-  if (!(h)) return FLOW2D_ERR_INVALID_ARGUMENT;              \
-  CU_TRY((h), cudaSetDevice((h)->device))
 
 int flow2d_stage_blur(flow2d_handle* h, const float* d_in, float* d_out, size_t w, size_t hh, float sigma) {
   STAGE_PROLOGUE(h);

@@ -38,6 +38,7 @@ struct SolveArgs {
   int outer;                      // 1, or (resident mode, grid 1x1) the number of outer iterations
   int ow, oh;                     // output tile of one CTA (ow % 4 == 0)
   int halo_x, halo_y;             // region origin = tile origin - halo; halo_x % 4 == 0
+  int y0, y1;                     // rows of the level this launch produces (0, h unless the level is slabbed)
   unsigned long long* timing;     // debug: 8 globaltimer stamps per CTA (null = off)
   int pdl;                        // 1 = launched with programmatic stream serialization: the previous kernel on the
                                   // stream is the previous pass of this solve (it writes only du/dv/phi/ksi)

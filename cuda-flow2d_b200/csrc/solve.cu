@@ -166,8 +166,8 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   const int lx = 4 * (tid & 15);  // first column of the strip within the region
   const int w = a.w, h = a.h, pitch = a.pitch;
 
-  const int ox0 = blockIdx.x * a.ow, oy0 = blockIdx.y * a.oh;
-  const int ox1 = min(w, ox0 + a.ow), oy1 = min(h, oy0 + a.oh);
+  const int ox0 = blockIdx.x * a.ow, oy0 = a.y0 + blockIdx.y * a.oh;
+  const int ox1 = min(w, ox0 + a.ow), oy1 = min(a.y1, oy0 + a.oh);
   const int gx = ox0 - a.halo_x + lx;  // multiple of 4
   const int gy = oy0 - a.halo_y + row;
   const int soff = row * LW + lx;
@@ -515,7 +515,7 @@ template <bool GRAD>
 __global__ void __launch_bounds__(NT, 1) solve_pass_kernel(const SolveArgs a) {
   extern __shared__ __align__(16) float sm[];
   // does this CTA's region reach the image border (or beyond)?
-  const int lx0 = blockIdx.x * a.ow - a.halo_x, ly0 = blockIdx.y * a.oh - a.halo_y;
+  const int lx0 = blockIdx.x * a.ow - a.halo_x, ly0 = a.y0 + blockIdx.y * a.oh - a.halo_y;
   const bool border = lx0 <= 0 || lx0 + LW >= a.w || ly0 <= 0 || ly0 + (int)(blockDim.x >> 4) >= a.h;
   if (border) pass_body<GRAD, true>(a, sm);
   else pass_body<GRAD, false>(a, sm);

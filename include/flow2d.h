@@ -152,6 +152,36 @@ FLOW2D_API int flow2d_stage_median(flow2d_handle* h, const float* d_in, float* d
 FLOW2D_API int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b, float* d_out,
                             size_t w, size_t h_, size_t radius);
 
+/* ---- one large frame on several GPUs: row-slab decomposition of the solve ----------------------
+ * (no counterpart upstream: the reference is single-GPU; SURVEY.md 8e, BASELINE.json configs[4]).
+ * One process / handle per GPU, every rank holds both full frames.  Pyramid levels with at least
+ * min_rows_per_rank rows per rank are slabbed: each rank runs the solve passes (99 % of the work)
+ * only on its own rows plus `ghost` rows on either side, exchanging ghost rows of the increment with
+ * its two neighbours every few outer iterations and gathering the increment at the end of the level.
+ * Everything else (restriction, warp, derivatives, add + median, the small levels) is computed
+ * redundantly by every rank.  The Jacobi scheme makes the result bit-identical to a single GPU.
+ * The transport is the caller's: `exchange` is called on the host, in stream order of the handle's
+ * stream, with
+ *   op 0 (halo):   send rows [own_y0, own_y0+ghost) to rank-1 and [own_y1-ghost, own_y1) to rank+1,
+ *                  receive rows [own_y0-ghost, own_y0) from rank-1 and [own_y1, own_y1+ghost) from rank+1
+ *   op 1 (gather): afterwards every rank must hold rows [0, height) of both fields; rank r contributes
+ *                  rows [r*b + min(r,e), ...) with b = height / world, e = height % world (+1 row for r < e)
+ * for the two device containers d_du, d_dv (row pitch pitch_elems floats).  It returns 0 on success. */
+typedef int (*flow2d_slab_exchange_fn)(void* user, int op, float* d_du, float* d_dv, size_t pitch_elems,
+                                       size_t width, size_t height, size_t own_y0, size_t own_y1, size_t ghost);
+typedef struct flow2d_slab {
+  int rank, world;
+  flow2d_slab_exchange_fn exchange;
+  void* user;
+  size_t min_rows_per_rank;  /* 0 = default (128) */
+} flow2d_slab;
+FLOW2D_API int flow2d_compute_slab_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
+                               float* d_flow_u, float* d_flow_v, const flow2d_params* p, const flow2d_slab* slab);
+/* flow2d_stage_solve on a slabbed level (for tests of the decomposition). */
+FLOW2D_API int flow2d_stage_solve_slab(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
+                            const float* d_flow_u, const float* d_flow_v, float* d_flow_du, float* d_flow_dv,
+                            size_t w, size_t h_, float hx, float hy, const flow2d_params* p, const flow2d_slab* slab);
+
 /* Debug aid, not part of the drop-in surface: every solve_pass CTA writes 8 %globaltimer stamps
  * (entry, loads+tensor, phi, weights, sweeps, stores) into d_stamps (device memory, >= 8 * CTAs of the
  * largest launch); NULL switches it off. */
