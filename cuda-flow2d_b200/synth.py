@@ -56,3 +56,26 @@ def smooth_random(w, h, seed, lo=-1.0, hi=1.0, cells=6):
     out = (g[y0, x0] * (1 - ax) * (1 - ay) + g[y0, x0 + 1] * ax * (1 - ay) +
            g[y0 + 1, x0] * (1 - ax) * ay + g[y0 + 1, x0 + 1] * ax * ay)
     return out.astype(np.float32)
+
+
+def make_pair_torch(w, h, seed, device, U0=(0.3, -0.2), U1=0.5, L=256.0, contrast=1.0, n=24):
+    """Same construction as make_pair, evaluated with torch on `device` (for frames too large for numpy
+    in reasonable time, e.g. 8192x8192).  Returns float32 torch tensors (frame0, frame1) on `device`."""
+    import torch
+    fx, fy, amp, phase = texture_params(seed, n)
+    ys = torch.arange(h, dtype=torch.float64, device=device).view(h, 1)
+    xs = torch.arange(w, dtype=torch.float64, device=device).view(1, w)
+    rng = np.random.default_rng(seed + 7919)
+    q = rng.uniform(0, 2 * np.pi, 4)
+    u = U0[0] + U1 * torch.sin(2 * np.pi * xs / L + q[0]) * torch.cos(2 * np.pi * ys / L + q[1])
+    v = U0[1] + U1 * torch.sin(2 * np.pi * xs / L + q[2]) * torch.cos(2 * np.pi * ys / L + q[3])
+    scale = 119.5 / (2.2 * np.sqrt((amp ** 2).sum() / 2))
+
+    def tex(x, y):
+        acc = torch.zeros((h, w), dtype=torch.float64, device=device)
+        for k in range(n):
+            acc += amp[k] * torch.sin(2 * np.pi * (fx[k] * x + fy[k] * y) + phase[k])
+        return (127.5 + contrast * scale * acc).to(torch.float32)
+    f0 = tex(xs.expand(h, w), ys.expand(h, w))
+    f1 = tex(xs - u, ys - v)
+    return f0, f1
