@@ -169,6 +169,16 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   a.timing = h->timing;
   a.y0 = 0; a.y1 = g.h;
 
+  // tiny levels (<= 1024 pixels): one CTA, one thread per pixel, all outer iterations in the kernel
+  if (p->resident_levels >= 0 && p->resident_levels != 2 && solve_tiny_fits(g.w, g.h)) {
+    a.du_in = a.dv_in = nullptr;
+    a.phi_in = a.ksi_in = nullptr;
+    a.du_out = du_a; a.dv_out = dv_a;
+    a.phi_out = want_phi ? phi : nullptr; a.ksi_out = want_phi ? ksi : nullptr;
+    a.sweeps = inner; a.outer = outer;
+    launch_solve_tiny(h->stream, a, grad);
+    return check_launch(h, "solve_tiny", 1);
+  }
   // resident mode: the whole level (plus a one-cell apron) fits one CTA's region
   const bool fits = g.w + 4 + 1 <= kSolveLW && g.h + 1 + 1 <= kSolveLH;
   if (fits && p->resident_levels >= 0) {

@@ -49,4 +49,8 @@ cudaError_t solve_pass_configure();
 // rows > 0: launch only that many region rows (resident mode of a level with few rows)
 void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows = 0);
 
+// whole solve of a level of <= 1024 pixels in one CTA, one thread per pixel (a.outer, a.sweeps = inner)
+bool solve_tiny_fits(int w, int h);
+void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad);
+
 }  // namespace flow2d

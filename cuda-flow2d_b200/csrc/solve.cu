@@ -546,4 +546,129 @@ void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_
   else cudaLaunchKernelEx(&cfg, solve_pass_kernel<false>, a);
 }
 
+// ---------------------------------------------------------------------------------------------
+// solve_tiny: the whole solve of a level of at most 1024 pixels (the coarsest ~20 levels of every
+// pyramid) in one CTA with ONE THREAD PER PIXEL.  Those levels are pure latency: with one pixel per
+// thread every per-pixel constant stays in registers, a sweep is ~50 dependent instructions and
+// four shared-memory reads, and the mirrored border is folded into four precomputed neighbour
+// indices.  Same arithmetic, operation for operation, as solve_pass.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTinyMax = 1024;
+
+__device__ __forceinline__ float div_rn1(float a, float d, float r) {
+  const float q0 = a * r;
+  float q = fmaf(r, fmaf(-d, q0, a), q0);
+  if (!(r != 0.f && in_fast_range(a))) q = (a == 0.f && r != 0.f) ? q0 : slow_div(a, d);
+  return q;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(kTinyMax, 1) solve_tiny_kernel(const SolveArgs a) {
+  __shared__ float sU[kTinyMax], sV[kTinyMax], sDU[kTinyMax], sDV[kTinyMax], sPHI[kTinyMax];
+  __shared__ float sSU[2][kTinyMax], sSV[2][kTinyMax];
+  const int w = a.w, h = a.h, n = w * h;
+  const int t = threadIdx.x;
+  const bool on = t < n;
+  const int x = on ? t % w : 0, y = on ? t / w : 0;
+  // mirrored neighbours (index -1 -> 1, n -> n-2)
+  const int il = y * w + (x == 0 ? 1 : x - 1), ir = y * w + (x == w - 1 ? w - 2 : x + 1);
+  const int iu = (y == 0 ? 1 : y - 1) * w + x, id = (y == h - 1 ? h - 2 : y + 1) * w + x;
+  const size_t g = (size_t)y * a.pitch + x;
+
+  float uc = 0.f, vc = 0.f, fx = 0.f, fy = 0.f, ft = 0.f, du = 0.f, dv = 0.f;
+  float J11 = 0.f, J22 = 0.f, nJ12 = 0.f, nJ13 = 0.f, nJ23 = 0.f;
+  if (on) {
+    uc = a.u[g]; vc = a.v[g]; fx = a.fx[g]; fy = a.fy[g]; ft = a.ft[g];
+    if (a.du_in) { du = a.du_in[g]; dv = a.dv_in[g]; }
+    if (GRAD) {
+      J11 = a.J[0][g]; J22 = a.J[1][g]; nJ12 = -a.J[2][g]; nJ13 = -a.J[3][g]; nJ23 = -a.J[4][g];
+    } else {
+      J11 = fx * fx; J22 = fy * fy; nJ12 = -(fx * fy); nJ13 = -(fx * ft); nJ23 = -(fy * ft);
+    }
+    sU[t] = uc; sV[t] = vc;
+  }
+  const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
+  const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
+  const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
+  const float wxp = hx_2 * ((x < w - 1) ? 1.f : 0.f), wxm = hx_2 * ((x > 0) ? 1.f : 0.f);
+  const float wyp = hy_2 * ((y < h - 1) ? 1.f : 0.f), wym = hy_2 * ((y > 0) ? 1.f : 0.f);
+
+  for (int outer = 0; outer < a.outer; ++outer) {
+    if (on) { sDU[t] = du; sDV[t] = dv; }
+    __syncthreads();
+    float phi = 0.f, ksi = 0.f;
+    if (on) {
+      // solve_2d.cu:141-162
+      const float dux = div_rn1(((sU[ir] - sU[il]) + sDU[ir]) - sDU[il], hx2, rhx2);
+      const float duy = div_rn1(((sU[id] - sU[iu]) + sDU[id]) - sDU[iu], hy2, rhy2);
+      const float dvx = div_rn1(((sV[ir] - sV[il]) + sDV[ir]) - sDV[il], hx2, rhx2);
+      const float dvy = div_rn1(((sV[id] - sV[iu]) + sDV[id]) - sDV[iu], hy2, rhy2);
+      float s = duy * duy;
+      s = fmaf(dux, dux, s);
+      s = fmaf(dvx, dvx, s);
+      s = fmaf(dvy, dvy, s);
+      s = fmaf(a.e_smooth, a.e_smooth, s);
+      const float r = sqrtf(s);
+      phi = 1.f / (r + r);
+      // solve_2d.cu:176-196: always the brightness tensor
+      const float j11 = fx * fx, j22 = fy * fy, j12 = fx * fy, j13 = fx * ft, j23 = fy * ft;
+      const float ta = j13 + fmaf(j11, du, j12 * dv);
+      const float tb = j23 + fmaf(j12, du, j22 * dv);
+      const float tc = fmaf(ft, ft, fmaf(j13, du, j23 * dv));
+      float sq = fmaf(du, ta, dv * tb) + tc;
+      sq = sq * ((sq > 0.f) ? 1.f : 0.f);
+      const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
+      ksi = 1.f / (q + q);
+      sPHI[t] = phi;
+    }
+    __syncthreads();
+    float axp = 0.f, axm = 0.f, ayp = 0.f, aym = 0.f, denU = 1.f, denV = 1.f, rU = 0.f, rV = 0.f;
+    if (on) {
+      // solve_2d.cu:333-349, 363, 367
+      axp = wxp * ((sPHI[ir] + phi) * 0.5f);
+      axm = wxm * ((sPHI[il] + phi) * 0.5f);
+      ayp = wyp * ((sPHI[id] + phi) * 0.5f);
+      aym = wym * ((sPHI[iu] + phi) * 0.5f);
+      const float sumH = ((axp + axm) + ayp) + aym;
+      denU = fmaf(J11, ksi, sumH);
+      denV = fmaf(J22, ksi, sumH);
+      rU = fast_path_rcp(denU);
+      rV = fast_path_rcp(denV);
+      sSU[0][t] = uc + du;
+      sSV[0][t] = vc + dv;
+      if (a.phi_out && outer == a.outer - 1) { a.phi_out[g] = phi; a.ksi_out[g] = ksi; }
+    }
+    __syncthreads();
+    for (int k = 0; k < a.sweeps; ++k) {
+      const float* cu = sSU[k & 1];
+      const float* cv = sSV[k & 1];
+      if (on) {
+        // solve_2d.cu:350-367 as compiled: mul, then fma chain xm, xp, yp, ym
+        float sumU = axm * (cu[il] - uc);
+        sumU = fmaf(axp, cu[ir] - uc, sumU);
+        sumU = fmaf(ayp, cu[id] - uc, sumU);
+        sumU = fmaf(aym, cu[iu] - uc, sumU);
+        float sumV = axm * (cv[il] - vc);
+        sumV = fmaf(axp, cv[ir] - vc, sumV);
+        sumV = fmaf(ayp, cv[id] - vc, sumV);
+        sumV = fmaf(aym, cv[iu] - vc, sumV);
+        du = div_rn1(fmaf(ksi, fmaf(nJ12, dv, nJ13), sumU), denU, rU);
+        dv = div_rn1(fmaf(ksi, fmaf(nJ12, du, nJ23), sumV), denV, rV);
+        sSU[(k + 1) & 1][t] = uc + du;
+        sSV[(k + 1) & 1][t] = vc + dv;
+      }
+      __syncthreads();
+    }
+  }
+  if (on) { a.du_out[g] = du; a.dv_out[g] = dv; }
+}
+
+bool solve_tiny_fits(int w, int h) { return w >= 2 && h >= 2 && w * h <= kTinyMax; }
+
+void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad) {
+  const int threads = (a.w * a.h + 31) / 32 * 32;
+  if (grad) solve_tiny_kernel<true><<<1, threads, 0, st>>>(a);
+  else solve_tiny_kernel<false><<<1, threads, 0, st>>>(a);
+}
+
 }  // namespace flow2d

@@ -64,7 +64,8 @@ typedef struct flow2d_params {
   float  gaussian_sigma;         /* "gaussian_sigma"         settings.xml Model@sigma; <= 0 = off */
   /* scheduling (0 = automatic); results are identical for every value */
   int    sweeps_per_pass;        /* Jacobi sweeps fused into one solve_pass launch (1..FLOW2D_MAX_SWEEPS_PER_PASS) */
-  int    resident_levels;        /* 0 auto / 1 = run small levels in a single resident CTA / -1 = never */
+  int    resident_levels;        /* 0 auto (one-thread-per-pixel CTA for levels <= 1024 px, resident solve_pass CTA for
+                                    levels <= 59x46, tiled passes otherwise) / 2 = no one-thread-per-pixel kernel / -1 = always tiled */
 } flow2d_params;
 
 #define FLOW2D_MAX_SWEEPS_PER_PASS 7

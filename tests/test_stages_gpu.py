@@ -125,9 +125,13 @@ def _run_solve(pkg, torch, fl, f0, f1, u, v, w, h, hx, hy, params):
 SOLVE_CASES = [
     # w, h, hx, hy, outer, inner
     (37, 29, 1.0, 1.0, 2, 3),          # resident (single CTA)
-    (5, 4, 116.8, 97.0, 3, 5),         # coarsest rub level
-    (59, 62, 1.25, 1.5, 2, 5),         # largest resident level
-    (60, 62, 1.0, 1.0, 2, 5),          # one column too wide for resident mode -> tiled
+    (5, 4, 116.8, 97.0, 3, 5),         # coarsest rub level: solve_tiny (one thread per pixel)
+    (32, 32, 1.0, 1.0, 3, 5),          # largest square solve_tiny level
+    (38, 26, 15.4, 14.9, 4, 5),        # solve_tiny, ragged
+    (2, 2, 1.0, 1.0, 2, 2),            # smallest level the path accepts
+    (59, 46, 1.25, 1.5, 2, 5),         # largest resident level
+    (60, 46, 1.0, 1.0, 2, 5),          # one column too wide for resident mode -> tiled
+    (59, 47, 1.0, 1.0, 2, 5),          # one row too high for resident mode -> tiled
     (131, 67, 2.92, 2.425, 2, 5),      # tiled, ragged
     (200, 150, 1.0, 1.0, 3, 5),        # tiled, several CTAs
     (96, 120, 1.0, 1.0, 1, 12),        # inner > sweeps per pass: phi/ksi stored and reloaded
@@ -162,10 +166,14 @@ def test_solve_is_independent_of_the_schedule(pkg, synth, torch_, sweeps):
     assert _eq(got[0], base[0]) and _eq(got[1], base[1])
 
 
-def test_resident_equals_tiled(pkg, synth, torch_):
-    w, h = 48, 40
+@pytest.mark.parametrize("w,h", [(48, 40), (30, 24), (12, 9)])
+def test_tiny_resident_and_tiled_agree(pkg, synth, torch_, w, h):
+    """resident_levels: 0 = automatic (solve_tiny for <= 1024 px, else resident solve_pass, else tiled),
+    2 = resident solve_pass even for tiny levels, -1 = always tiled."""
     f0, f1, u, v = _solve_inputs(synth, w, h, 9)
     fl = pkg.Flow2D(w, h)
-    a = _run_solve(pkg, torch_, fl, f0, f1, u, v, w, h, 1.3, 1.1, pkg.default_params(outer=4, inner=5, resident_levels=0))
-    b = _run_solve(pkg, torch_, fl, f0, f1, u, v, w, h, 1.3, 1.1, pkg.default_params(outer=4, inner=5, resident_levels=-1))
-    assert _eq(a[0], b[0]) and _eq(a[1], b[1])
+    r = [_run_solve(pkg, torch_, fl, f0, f1, u, v, w, h, 1.3, 1.1, pkg.default_params(outer=4, inner=5, resident_levels=m))
+         for m in (0, 2, -1)]
+    for other in r[1:]:
+        for k in range(4):
+            assert _eq(r[0][k], other[k])
