@@ -134,6 +134,32 @@ def test_solve_vs_reference_grey(pkg, oracle, synth, ref, torch_, w, h, hx, hy, 
     assert _eq(odu, rdu) and _eq(odv, rdv), "oracle expected bit exact with the reference"
 
 
+@pytest.mark.parametrize("w,h,hx,hy,outer,inner", [(64, 48, 1.0, 1.0, 2, 5), (128, 96, 1.5, 1.25, 3, 5), (131, 67, 2.92, 2.425, 2, 5)])
+def test_solve_vs_reference_gradient(pkg, oracle, synth, ref, torch_, w, h, hx, hy, outer, inner):
+    """Gradient constancy (solve_2d_grad): the reference result depends on its 16x8 CUDA tiling, which is
+    reproduced, and next to partial blocks it reads uninitialised shared memory, which
+    cannot be.  Sizes that are multiples of 16x8 must match everywhere; otherwise the comparison covers
+    the pixels that the undefined cells (last column / row) cannot reach within outer*inner sweeps."""
+    f0, f1, _, _ = synth.make_pair(w, h, 400 + w, U1=1.5, L=48.0)
+    u = synth.smooth_random(w, h, 11, -2, 2)
+    v = synth.smooth_random(w, h, 12, -2, 2)
+    alpha = 5.0
+    rdu, rdv, rphi, rksi = ref.solve(f0, f1, u, v, hx, hy, alpha, 0.001, 0.001, outer, inner, 1)
+    fl = pkg.Flow2D(w, h, constancy=1)
+    d = [fl.to_container(a) for a in (f0, f1, u, v)]
+    t = [fl.container(float("nan")) for _ in range(4)]
+    fl.stage_solve(d[0], d[1], d[2], d[3], t[0], t[1], t[2], t[3], w, h, hx, hy, pkg.default_params(outer=outer, inner=inner, alpha=alpha))
+    torch_.cuda.synchronize()
+    gdu, gdv = fl.from_container(t[0], w, h), fl.from_container(t[1], w, h)
+    op = oracle.make_params(outer=outer, inner=inner, alpha=alpha, constancy=oracle.GRADIENT)
+    odu, odv, _, _ = oracle.solve_level(f0, f1, u, v, hx, hy, op)
+    assert _eq(gdu, odu) and _eq(gdv, odv), "kernel vs oracle (gradient)"
+    reach = 0 if (w % 16 == 0 and h % 8 == 0) else outer * inner + 1
+    ys, xs = slice(0, h - reach), slice(0, w - reach)
+    print(_rep("gradient du, full frame", gdu, rdu))
+    assert _eq(gdu[ys, xs], rdu[ys, xs]) and _eq(gdv[ys, xs], rdv[ys, xs])
+
+
 C1B = dict(levels=50, scale=0.9, outer=40, inner=5, alpha=35.0, e_smooth=0.001, e_data=0.001, median=5, sigma=1.5)
 C1A = dict(levels=20, scale=0.9, outer=20, inner=5, alpha=3.5, e_smooth=0.001, e_data=0.001, median=5, sigma=0.45)
 
