@@ -6,6 +6,9 @@
 // Outputs: <out><counter>flow-u-W-H.raw, flow-v-W-H.raw (float32), res.pgm (colour-coded flow, binary PPM),
 // amp-W-H.raw (float32 magnitude).
 // Exit codes: 0 ok / usage, 1 no CUDA device, 2 input files unreadable, 3 settings unreadable.
+//   cuda-flow2d --sequence <width> <height> <output path> <frame 0> <frame 1> ... <frame N>   (new)
+//       flow between every pair of consecutive frames of a sequence, several pairs in flight at once
+//       (flow2d_compute_async on 4 handles); writes <out>NNNN_flow-u-W-H.raw / NNNN_flow-v-W-H.raw
 // Differences: no getchar() at exit; the 8-bit reader is wired to Mode@imageType="8-bit";
 // files are also looked up under Input/Path@inputPath when they are not found in the CWD.
 #include <cmath>
@@ -22,6 +25,53 @@
 
 using std::string;
 
+// Sequence mode: the X-ray-radiography use case of the reference README (one flow per consecutive
+// frame pair).  K handles, one stream each; pair i runs on handle i % K, and its result is written
+// while the other handles keep computing.
+static int run_sequence(int argc, char** argv) {
+  if (argc < 7) {
+    std::cout << "Usage: " << argv[0] << " --sequence <width> <height> <output path> <frame 0> <frame 1> [...]" << std::endl;
+    return 0;
+  }
+  const size_t width = std::atoi(argv[2]), height = std::atoi(argv[3]);
+  const string out = argv[4];
+  const int n_frames = argc - 5, n_pairs = n_frames - 1;
+  const int K = n_pairs < 4 ? n_pairs : 4;
+  flow2d_params p;
+  flow2d_default_params(&p);  // src/main.cpp:70-80
+  std::vector<flow2d_handle*> handles(K, nullptr);
+  for (int k = 0; k < K; k++)
+    if (flow2d_create(&handles[k], 0, width, height, FLOW2D_GREY) != FLOW2D_OK) return 1;
+  std::vector<Data2D> frames(n_frames);
+  for (int i = 0; i < n_frames; i++)
+    if (!frames[i].ReadRAWFromFileF32(argv[5 + i], width, height)) return 2;
+  std::vector<Data2D*> us(K), vs(K);
+  for (int k = 0; k < K; k++) { us[k] = new Data2D(width, height); vs[k] = new Data2D(width, height); }
+  const string suffix = "-" + std::to_string(width) + "-" + std::to_string(height) + ".raw";
+  auto flush = [&](int pair) {
+    const int k = pair % K;
+    flow2d_synchronize(handles[k]);
+    char tag[16];
+    std::snprintf(tag, sizeof tag, "%04d_", pair);
+    us[k]->WriteRAWToFileF32((out + tag + "flow-u" + suffix).c_str());
+    vs[k]->WriteRAWToFileF32((out + tag + "flow-v" + suffix).c_str());
+  };
+  int rc = 0;
+  for (int i = 0; i < n_pairs && rc == 0; i++) {
+    const int k = i % K;
+    if (i >= K) flush(i - K);  // the handle's previous pair must be on disk before its buffers are reused
+    if (flow2d_compute_async(handles[k], frames[i].DataPtr(), frames[i + 1].DataPtr(), us[k]->DataPtr(), vs[k]->DataPtr(), &p) !=
+        FLOW2D_OK) {
+      std::fprintf(stderr, "Error: %s\n", flow2d_last_error(handles[k]));
+      rc = 1;
+    }
+  }
+  for (int i = (n_pairs > K ? n_pairs - K : 0); i < n_pairs && rc == 0; i++) flush(i);
+  std::printf("Sequence: %d frame pairs of %zux%zu on %d concurrent handles\n", n_pairs, width, height, K);
+  for (int k = 0; k < K; k++) { delete us[k]; delete vs[k]; flow2d_destroy(handles[k]); }
+  return rc;
+}
+
 static bool exists(const string& p) {
   std::FILE* f = std::fopen(p.c_str(), "rb");
   if (f) std::fclose(f);
@@ -32,6 +82,8 @@ int main(int argc, char** argv) {
   std::printf("//----------------------------------------------------------------------//\n");
   std::printf("//   2D optical flow, Blackwell-native (%s)   //\n", flow2d_version());
   std::printf("//----------------------------------------------------------------------//\n");
+
+  if (argc >= 2 && string(argv[1]) == "--sequence") return run_sequence(argc, argv);
 
   size_t width = 584, height = 388;
   size_t warp_levels_count = 50;  // src/main.cpp:70-80

@@ -66,3 +66,24 @@ def test_settings_form_8bit_and_exit_codes(rub, oracle, tmp_path):
     assert _run(CLI, ["missing.xml"], tmp_path).returncode == 3
     assert _run(CLI, ["nope1.raw", "nope2.raw", 584, 388, "x_", "out/"], tmp_path).returncode == 2
     assert _run(CLI, ["a", "b", "c"], tmp_path).returncode == 0
+
+
+def test_sequence_mode_equals_pairwise(synth, oracle, tmp_path):
+    """--sequence: flows between consecutive frames, several pairs in flight on concurrent handles;
+    every pair must equal the single-pair result (= oracle) bit for bit."""
+    w, h, n = 96, 80, 7
+    (tmp_path / "out").mkdir()
+    frames = []
+    for i in range(n):
+        f, _, _, _ = synth.make_pair(w, h, 100, U0=(0.4 * i, -0.2 * i), U1=0.0)  # the texture translating steadily
+        frames.append(f)
+        f.tofile(tmp_path / ("frame%02d.raw" % i))
+    names = ["frame%02d.raw" % i for i in range(n)]
+    r = _run(CLI, ["--sequence", w, h, "out/"] + names, tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    p = oracle.make_params()
+    for i in range(n - 1):
+        u = np.fromfile(tmp_path / "out" / ("%04d_flow-u-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+        v = np.fromfile(tmp_path / "out" / ("%04d_flow-v-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+        ou, ov = oracle.compute_flow(frames[i], frames[i + 1], p)
+        assert np.all(u == ou) and np.all(v == ov), "pair %d" % i
