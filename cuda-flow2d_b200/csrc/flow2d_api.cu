@@ -284,8 +284,29 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       a.y0 = va; a.y1 = vb;
       a.pdl = (pass > 0 && !no_pdl && !after_exchange) ? 1 : 0;  // the first pass follows the derivatives kernel
       after_exchange = false;
-      launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
-      TRY(check_launch(h, "solve_pass", 1));
+      // Mid-size levels cannot fill the GPU with 64x48 regions; there the latency of one CTA is what
+      // counts and the one-thread-per-pixel pass (32x32 regions) is faster as long as its many more
+      // CTAs still fit a few waves.  Measured per wave on B200: ~3.5 us against ~11 us.
+      bool small = false;
+      if (npass == 1 && p->resident_levels != 2 && p->resident_levels != -1) {
+        const int so = kSmallTS - 2 * (s + 1);
+        if (so >= 8) {
+          const long long n_small = (long long)((g.w + so - 1) / so) * ((vb - va + so - 1) / so);
+          const long long n_big = (long long)((g.w + a.ow - 1) / a.ow) * ((vb - va + a.oh - 1) / a.oh);
+          const double t_small = (double)((n_small + 147) / 148) * 3.5, t_big = (double)((n_big + 147) / 148) * 11.0;
+          small = t_small < t_big;
+          if (small) {
+            a.halo_x = a.halo_y = s + 1;
+            a.ow = a.oh = so;
+            launch_solve_small_pass(h->stream, a, grad, (g.w + so - 1) / so, (vb - va + so - 1) / so);
+            TRY(check_launch(h, "solve_small_pass", 1));
+          }
+        }
+      }
+      if (!small) {
+        launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
+        TRY(check_launch(h, "solve_pass", 1));
+      }
       cur_du = a.du_out; cur_dv = a.dv_out;
     }
   }

@@ -49,6 +49,10 @@ cudaError_t solve_pass_configure();
 // rows > 0: launch only that many region rows (resident mode of a level with few rows)
 void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows = 0);
 
+// one pass of a mid-size level with one thread per pixel: 32x32 regions, a.halo_x = a.halo_y = a.sweeps + 1,
+// a.ow = a.oh = kSmallTS - 2 * halo; phi/ksi are always computed in the pass (a.phi_in must be null)
+constexpr int kSmallTS = 32;
+void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y);
 // whole solve of a level of <= 1024 pixels in one CTA, one thread per pixel (a.outer, a.sweeps = inner)
 bool solve_tiny_fits(int w, int h);
 void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad);

@@ -166,6 +166,18 @@ def test_solve_is_independent_of_the_schedule(pkg, synth, torch_, sweeps):
     assert _eq(got[0], base[0]) and _eq(got[1], base[1])
 
 
+@pytest.mark.parametrize("w,h,inner", [(131, 67, 5), (200, 150, 5), (333, 250, 3), (64, 64, 1), (100, 90, 7)])
+def test_small_pass_equals_solve_pass(pkg, synth, torch_, w, h, inner):
+    """Mid-size levels: the one-thread-per-pixel pass (32x32 regions, chosen automatically) and the
+    64x48-region solve_pass (resident_levels = -1 forces it) must give the same bits."""
+    f0, f1, u, v = _solve_inputs(synth, w, h, 21)
+    fl = pkg.Flow2D(w, h)
+    a = _run_solve(pkg, torch_, fl, f0, f1, u, v, w, h, 1.7, 1.4, pkg.default_params(outer=3, inner=inner, resident_levels=0))
+    b = _run_solve(pkg, torch_, fl, f0, f1, u, v, w, h, 1.7, 1.4, pkg.default_params(outer=3, inner=inner, resident_levels=-1))
+    for k in range(4):
+        assert _eq(a[k], b[k])
+
+
 @pytest.mark.parametrize("w,h", [(48, 40), (30, 24), (12, 9)])
 def test_tiny_resident_and_tiled_agree(pkg, synth, torch_, w, h):
     """resident_levels: 0 = automatic (solve_tiny for <= 1024 px, else resident solve_pass, else tiled),
