@@ -33,6 +33,7 @@ class Params(C.Structure):
         ("gaussian_sigma", C.c_float),
         ("sweeps_per_pass", C.c_int),
         ("resident_levels", C.c_int),
+        ("throughput_mode", C.c_int),
     ]
 
 

@@ -288,7 +288,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       // counts and the one-thread-per-pixel pass (32x32 regions) is faster as long as its many more
       // CTAs still fit a few waves.  Measured per wave on B200: ~3.5 us against ~11 us.
       bool small = false;
-      if (npass == 1 && p->resident_levels != 2 && p->resident_levels != -1) {
+      if (npass == 1 && p->resident_levels != 2 && p->resident_levels != -1 && !p->throughput_mode) {
         const int so = kSmallTS - 2 * (s + 1);
         if (so >= 8) {
           const long long n_small = (long long)((g.w + so - 1) / so) * ((vb - va + so - 1) / so);
@@ -448,6 +448,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   key.p.equation_data = p->equation_data; key.p.median_radius = p->median_radius;
   key.p.gaussian_sigma = p->gaussian_sigma; key.p.sweeps_per_pass = p->sweeps_per_pass;
   key.p.resident_levels = p->resident_levels;
+  key.p.throughput_mode = p->throughput_mode;
   key.timing = h->timing;
   if (h->graph_exec && std::memcmp(&key, h->graph_key, sizeof key) == 0) {
     CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
@@ -529,6 +530,7 @@ void flow2d_default_params(flow2d_params* p) {
   p->gaussian_sigma = 1.5f;
   p->sweeps_per_pass = 0;
   p->resident_levels = 0;
+  p->throughput_mode = 0;
 }
 
 size_t flow2d_max_warp_level(size_t width, size_t height, float scale_factor) {

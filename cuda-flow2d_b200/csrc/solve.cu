@@ -131,6 +131,7 @@ __device__ __forceinline__ void div_rn4(const float (&a)[4], float d, float r, f
 
 struct Strip {  // per-thread state that lives in registers during the sweeps
   float uc[4], vc[4], dv[4];
+  float ksi[4], nJ12[4];
   float su[4], sv[4];
   float ex[5];  // x edge weights: ex[i] lies between pixels x-1+i and x+i
   bool den_ok;  // all eight denominators of the strip are safe for the fast division path
@@ -406,6 +407,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         rU[i] = fast_path_rcp(denU[i]);
         rV[i] = fast_path_rcp(denV[i]);
         t.den_ok = t.den_ok && rU[i] != 0.f && rV[i] != 0.f;
+        t.ksi[i] = ksi[i];
         t.su[i] = t.uc[i] + du[i];
         t.sv[i] = t.vc[i] + t.dv[i];
       }
@@ -417,6 +419,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
       st4(sm + P_RV * PL + soff, rV);
       st4(sm + P_SU0 * PL + soff, t.su);
       st4(sm + P_SV0 * PL + soff, t.sv);
+      unpack(ld4(sm + P_NJ12 * PL + soff), t.nJ12);
     }
     __syncthreads();
     stamp(a, 3);
@@ -465,9 +468,9 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         sumV[i] = fmaf(eym[i], nU[i] - v0, s);
       }
       // (-J13) - J12*dv is one FFMA in the reference SASS
-      float ksi[4], nJ12[4], nj[4], den[4], rcp[4], num[4], rdv[4];
-      unpack(ld4(sm + P_KSI * PL + soff), ksi);
-      unpack(ld4(sm + P_NJ12 * PL + soff), nJ12);
+      float nj[4], den[4], rcp[4], num[4], rdv[4];
+      const float (&ksi)[4] = t.ksi;
+      const float (&nJ12)[4] = t.nJ12;
       unpack(ld4(sm + P_NJ13 * PL + soff), nj);
       unpack(ld4(sm + P_DENU * PL + soff), den);
       unpack(ld4(sm + P_RU * PL + soff), rcp);

@@ -39,6 +39,7 @@ static int run_sequence(int argc, char** argv) {
   const int K = n_pairs < 4 ? n_pairs : 4;
   flow2d_params p;
   flow2d_default_params(&p);  // src/main.cpp:70-80
+  p.throughput_mode = K > 1;
   std::vector<flow2d_handle*> handles(K, nullptr);
   for (int k = 0; k < K; k++)
     if (flow2d_create(&handles[k], 0, width, height, FLOW2D_GREY) != FLOW2D_OK) return 1;

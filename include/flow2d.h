@@ -65,7 +65,10 @@ typedef struct flow2d_params {
   /* scheduling (0 = automatic); results are identical for every value */
   int    sweeps_per_pass;        /* Jacobi sweeps fused into one solve_pass launch (1..FLOW2D_MAX_SWEEPS_PER_PASS) */
   int    resident_levels;        /* 0 auto (one-thread-per-pixel CTA for levels <= 1024 px, resident solve_pass CTA for
-                                    levels <= 59x46, tiled passes otherwise) / 2 = no one-thread-per-pixel kernel / -1 = always tiled */
+                                    levels <= 59x46, tiled passes otherwise) / 2 = no one-thread-per-pixel kernels / -1 = always tiled */
+  int    throughput_mode;        /* 0 = schedule for the latency of ONE frame pair (mid-size levels use the one-thread-per-
+                                    pixel pass, which trades redundant halo work for a 3x shorter dependent chain);
+                                    1 = schedule for throughput: several handles share the GPU, redundant work is not free */
 } flow2d_params;
 
 #define FLOW2D_MAX_SWEEPS_PER_PASS 7
