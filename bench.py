@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the optical-flow hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1b|c4|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|rub_c1b|rub_c1a|c1b|c3|c4|c5] [--streams K] [--pairs P]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path (flow2d_compute*) over one frame pair per GPU.  Default
@@ -43,6 +44,14 @@ WORKLOADS = {
     "c1b": dict(name="C1b-shaped: synthetic 584x388 pair, reference main.cpp defaults (47 levels, 40x5, median 5, sigma 1.5)",
                 w=584, h=388, seed=1101, gen=dict(U0=(0.5, -0.3), U1=1.0, L=128.0),
                 cfg=dict(levels=50, scale=0.9, outer=40, inner=5, alpha=35.0, e_smooth=0.001, e_data=0.001, median=5, sigma=1.5)),
+    "rub_c1b": dict(name="C1b: the reference's bundled rub1/rub2 pair (584x388, 8-bit -> f32) with its main.cpp defaults "
+                         "(47 levels, 40x5, alpha 35, median 5, sigma 1.5) (BASELINE.json configs[0])", rub=True,
+                    w=584, h=388, seed=0, gen={},
+                    cfg=dict(levels=50, scale=0.9, outer=40, inner=5, alpha=35.0, e_smooth=0.001, e_data=0.001, median=5, sigma=1.5)),
+    "rub_c1a": dict(name="C1a: the bundled rub pair with the solver values of the reference's settings.xml "
+                         "(20 levels, 20x5, alpha 3.5, median 5, sigma 0.45) (BASELINE.json configs[0])", rub=True,
+                    w=584, h=388, seed=0, gen={},
+                    cfg=dict(levels=20, scale=0.9, outer=20, inner=5, alpha=3.5, e_smooth=0.001, e_data=0.001, median=5, sigma=0.45)),
     "c4": dict(name="C4: batch of 1024x1024 radiography-like pairs, reference main.cpp defaults (50 levels, 40x5); "
                     "16 pairs per step per GPU on 8 concurrent handles (one stream each)", streams=8, pairs=16,
                w=1024, h=1024, seed=4000, gen=dict(U0=(0.0, 0.0), U1=4.0, L=384.0, contrast=0.3, noise=2.0),
@@ -119,6 +128,9 @@ def measured_peak_gbs():
 
 
 def make_frames(wl, rank):
+    if wl.get("rub"):  # the reference's own frame pair, committed as a fixture (tests/golden/README.md)
+        z = np.load(os.path.join(ROOT, "tests", "golden", "rub_u8.npz"))
+        return z["rub1"].astype(np.float32), z["rub2"].astype(np.float32)
     from cuda_flow2d_b200 import synth
     g = dict(wl["gen"])
     return synth.make_pair(wl["w"], wl["h"], wl["seed"] + rank, **g)[:2]
