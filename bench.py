@@ -21,6 +21,7 @@ single level, 500 Jacobi sweeps.  Rank 0 prints ONE JSON lin
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -59,6 +60,10 @@ WORKLOADS = {
     "c3": dict(name="C3-Grey: synthetic 2048x2048 pair, full pyramid (50 levels, 40x5, median 5, sigma 1.5), alpha 3.5",
                w=2048, h=2048, seed=2001, gen=dict(U0=(3.0, -2.0), U1=6.0, L=512.0),
                cfg=dict(levels=50, scale=0.9, outer=40, inner=5, alpha=3.5, e_smooth=0.001, e_data=0.001, median=5, sigma=1.5)),
+    "c3g": dict(name="C3: synthetic 2048x2048 pair, full model: GRADIENT constancy + robust penalisers + flow-driven smoothness, "
+                     "full pyramid (50 levels, 40x5, median 5, sigma 1.5), alpha 3.5 (BASELINE.json configs[2])", gradient=True,
+                w=2048, h=2048, seed=2001, gen=dict(U0=(3.0, -2.0), U1=6.0, L=512.0),
+                cfg=dict(levels=50, scale=0.9, outer=40, inner=5, alpha=3.5, e_smooth=0.001, e_data=0.001, median=5, sigma=1.5)),
     "c5": dict(name="C5-Grey: single 8192x8192 pair, full pyramid (50 levels, 40x5, median 5, sigma 1.5), alpha 3.5; "
                     "solve slabbed by rows across the GPUs (halo exchange + per-level gather over NCCL)", slab=True,
                w=8192, h=8192, seed=5001, gen=dict(U0=(0.0, 0.0), U1=8.0, L=2048.0),
@@ -156,7 +161,7 @@ def run_reference(args, wl, rank, world):
             f1.tofile(b)
             cmd = [exe, "flow", a, b, w, h, "-", cfg["levels"], "%.9g" % cfg["scale"], cfg["outer"], cfg["inner"],
                    "%.9g" % cfg["alpha"], "%.9g" % cfg["e_smooth"], "%.9g" % cfg["e_data"], cfg["median"], "%.9g" % cfg["sigma"],
-                   0, args.warmup, args.steps]
+                   1 if wl.get("gradient") else 0, args.warmup, args.steps]
             r = subprocess.run([str(c) for c in cmd], stdin=subprocess.DEVNULL, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
             ms = [float(l.split()[2]) for l in r.stdout.decode().splitlines() if l.startswith("REF_MS timed")]
         if r.returncode != 0 or not ms:
@@ -185,7 +190,7 @@ def run_reference(args, wl, rank, world):
     else:
         # no reference build on this box: time the CPU port of the same algorithm on all host cores
         from oracle import oracle as O
-        p = O.make_params(**cfg)
+        p = O.make_params(constancy=1 if wl.get("gradient") else 0, **cfg)
         for _ in range(min(args.warmup, 1)):
             O.compute_flow(f0, f1, p)
         n = max(1, min(args.steps, 3))
@@ -232,7 +237,7 @@ def run_ours(args, wl, rank, world, local_rank):
     else:
         frames = [make_frames(wl, rank * 16 + i) for i in range(n_distinct)]
     f0, f1 = frames[0]
-    handles = [m.Flow2D(w, h, device=dev) for _ in range(K)]
+    handles = [m.Flow2D(w, h, constancy=m.GRADIENT if wl.get("gradient") else m.GREY, device=dev) for _ in range(K)]
     fl = handles[0]
     params = m.default_params(**cfg)
     params.throughput_mode = 1 if K > 1 else 0  # several handles share the GPU: redundant halo work is not free
@@ -285,6 +290,7 @@ def run_ours(args, wl, rank, world, local_rank):
         step_device()
     barrier()
     launches_per_step = fl.stats()["kernel_launches"] * P
+    launches_by_kernel = {k: v * P for k, v in fl.launch_counts().items()}
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
@@ -337,16 +343,17 @@ def run_ours(args, wl, rank, world, local_rank):
     d0, d1 = din[0]
 
     # ---- dominant kernel: solve_pass launch duration, measured live with events ----
-    roof = None
+    roof = warp_roof = None
     if rank == 0:
         g = m.level_geometry(w, h, cfg["scale"], 0)
         t = [fl.container(0.0) for _ in range(4)]
         sp = m.default_params(**cfg)
-        n0 = fl.stats()["kernel_launches"]
+        c0 = fl.launch_counts()
         with torch.cuda.stream(stream):
             fl.stage_solve(d0, d1, t[0], t[1], t[2], t[3], None, None, w, h, float(g[2]), float(g[3]), sp)
         torch.cuda.synchronize(dev)
-        n_pass = fl.stats()["kernel_launches"] - n0 - 1  # minus the derivatives kernel
+        used = {k: v - c0.get(k, 0) for k, v in fl.launch_counts().items() if k.startswith("solve") and v > c0.get(k, 0)}
+        kname, n_pass = max(used.items(), key=lambda kv: kv[1])  # the solver kernel of the finest level
         reps = 3
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
@@ -360,7 +367,37 @@ def run_ours(args, wl, rank, world, local_rank):
         alg_bytes = 40.0 * w * h  # one pass = 8 fields read + 2 written, 4 B each
         achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
         sweeps = cfg["outer"] * cfg["inner"] / n_pass
-        roof = {"kernel": "solve_pass_kernel<false> (%d launches per solve, %.3g Jacobi sweeps per launch on average)" % (n_pass, sweeps),
+        # second kernel BASELINE.json's metric names: backward warping, 16 B per pixel (u, v, frame 1 read; warped frame
+        # written), timed one launch at a time with the L2 flushed in between so that the bytes really come from HBM
+        # several buffer sets, together larger than twice the L2, launched back to back: every byte comes from HBM and
+        # the launch overhead is amortised as it is inside a pyramid
+        nsets = max(2, min(24, int(math.ceil(300e6 / (16.0 * fl.pitch * h)))))
+        sets = [[fl.container(0.0) for _ in range(4)] for _ in range(nsets)]
+        yy, xx = torch.meshgrid(torch.arange(h, device=d1.device, dtype=torch.float32),
+                                torch.arange(fl.pitch, device=d1.device, dtype=torch.float32), indexing="ij")
+        for q in sets:  # a smooth +-2 px flow, the magnitude of one pyramid level's update
+            q[0].copy_(d1)
+            q[1].copy_(2.0 * torch.sin(xx / 40.0) * torch.cos(yy / 50.0))
+            q[2].copy_(2.0 * torch.cos(xx / 30.0) * torch.sin(yy / 60.0))
+        del xx, yy
+        with torch.cuda.stream(stream):
+            for q in sets:  # warm-up
+                fl.stage_warp(d0, q[0], q[1], q[2], q[3], w, h, float(g[2]), float(g[3]))
+            a.record(stream)
+            for _ in range(3):
+                for q in sets:
+                    fl.stage_warp(d0, q[0], q[1], q[2], q[3], w, h, float(g[2]), float(g[3]))
+            b.record(stream)
+        torch.cuda.synchronize(dev)
+        warp_ms = a.elapsed_time(b) / (3 * nsets)
+        del sets
+        warp_roof = {"kernel": "warp_kernel", "bound": "hbm", "achieved": 16.0 * w * h / (warp_ms * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": 16.0 * w * h / (warp_ms * 1e-3) / 1e9 / peak, "launch_us": warp_ms * 1e3,
+                     "algorithmic_bytes_per_launch": 16.0 * w * h,
+                     "note": "finest level of the workload; %d buffer sets (%.0f MB, > 2 x L2) warped back to back so that "
+                             "every byte comes from HBM" % (nsets, nsets * 16.0 * fl.pitch * h / 1e6)}
+        roof = {"kernel": "%s_kernel<%s> (%d launches per solve, %.3g Jacobi sweeps per launch on average)" %
+                          (kname.replace("(resident)", ""), "true" if wl.get("gradient") else "false", n_pass, sweeps),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "launch_us": launch_ms * 1e3,
                 "algorithmic_bytes_per_launch": alg_bytes,
@@ -390,7 +427,7 @@ def run_ours(args, wl, rank, world, local_rank):
             scale = c["outer"] / 4.0
             c["outer"] = 4
             sample = "outer iterations cut to 4 of %d (same pyramid), time scaled x%.1f" % (cfg["outer"], scale)
-        p = O.make_params(**c)
+        p = O.make_params(constancy=1 if wl.get("gradient") else 0, **c)
         t0 = time.perf_counter()
         O.compute_flow(f0, f1, p)
         tc = (time.perf_counter() - t0) * scale
@@ -418,7 +455,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "gpu_launches": int(launches_per_step * args.steps),
             "wall_ms_per_step": t_wall / args.steps * 1e3,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
-            "roofline": roof, "cpu_baseline": cpu,
+            "launches_by_kernel": {k: int(v * args.steps) for k, v in launches_by_kernel.items()},
+            "roofline": roof, "roofline_warp": warp_roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if dist is not None:

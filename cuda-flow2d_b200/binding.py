@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 GREY, GRADIENT = 0, 1
+KERNEL_KINDS = 11  # FLOW2D_KERNEL_KINDS
 
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -74,6 +75,9 @@ def lib():
         L.flow2d_compute_async.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params)]
         L.flow2d_synchronize.argtypes = [vp]
         L.flow2d_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_int), fp]
+        L.flow2d_last_launch_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.flow2d_kernel_kind_name.argtypes = [C.c_int]
+        L.flow2d_kernel_kind_name.restype = C.c_char_p
         L.flow2d_max_warp_level.restype = sz
         L.flow2d_max_warp_level.argtypes = [sz, sz, C.c_float]
         L.flow2d_level_geometry.argtypes = [sz, sz, C.c_float, C.c_int, C.POINTER(sz), C.POINTER(sz), fp, fp]
@@ -163,6 +167,12 @@ class Flow2D:
         n, lv, ms = C.c_longlong(), C.c_int(), C.c_float()
         self._check(lib().flow2d_last_stats(self._h, C.byref(n), C.byref(lv), C.byref(ms)))
         return {"kernel_launches": n.value, "levels_run": lv.value, "device_ms": ms.value}
+
+    def launch_counts(self):
+        """Kernel launches of the last call, by kernel (flow2d_last_launch_counts)."""
+        counts = (C.c_longlong * KERNEL_KINDS)()
+        self._check(lib().flow2d_last_launch_counts(self._h, counts))
+        return {lib().flow2d_kernel_kind_name(k).decode(): int(counts[k]) for k in range(KERNEL_KINDS) if counts[k]}
 
     # -- containers (torch is only the allocator) --
     def container(self, fill=None):

@@ -47,12 +47,14 @@ struct flow2d_handle {
   float* pool = nullptr;
   float* c[C_COUNT] = {};
   long long launches = 0;
+  long long kind_launches[FLOW2D_KERNEL_KINDS] = {};
   int levels_run = 0;
   float device_ms = 0.f;
   unsigned long long* timing = nullptr;  // debug: phase stamps of solve_pass (flow2d_debug_timing)
   cudaGraphExec_t graph_exec = nullptr;  // captured level schedule of the last (buffers, parameters) combination
   unsigned char graph_key[128] = {};
   long long graph_launches = 0;
+  long long graph_kind_launches[FLOW2D_KERNEL_KINDS] = {};
   int graph_levels = 0;
   std::string err;
 };
@@ -79,11 +81,20 @@ int fail(flow2d_handle* h, int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                         \
   } while (0)
 
-int check_launch(flow2d_handle* h, const char* what, int kernels) {
+const char* const kKindNames[FLOW2D_KERNEL_KINDS] = {"blur", "resample", "warp", "derivatives", "grad_tensor", "solve_pass",
+                                                      "solve_pass(resident)", "solve_small_pass", "solve_tiny", "add_median",
+                                                      "add"};
+
+int check_launch(flow2d_handle* h, int kind, int kernels) {
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(h, FLOW2D_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(h, FLOW2D_ERR_CUDA, "launch of %s failed: %s", kKindNames[kind], cudaGetErrorString(e));
   h->launches += kernels;
+  h->kind_launches[kind] += kernels;
   return FLOW2D_OK;
+}
+void reset_launch_counts(flow2d_handle* h) {
+  h->launches = 0;
+  for (auto& k : h->kind_launches) k = 0;
 }
 
 #define TRY(expr)              \
@@ -177,7 +188,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
     a.phi_out = want_phi ? phi : nullptr; a.ksi_out = want_phi ? ksi : nullptr;
     a.sweeps = inner; a.outer = outer;
     launch_solve_tiny(h->stream, a, grad);
-    return check_launch(h, "solve_tiny", 1);
+    return check_launch(h, FLOW2D_K_SOLVE_TINY, 1);
   }
   // resident mode: the whole level (plus a one-cell apron) fits one CTA's region
   const bool fits = g.w + 4 + 1 <= kSolveLW && g.h + 1 + 1 <= kSolveLH;
@@ -189,7 +200,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
     a.sweeps = inner; a.outer = outer;
     a.ow = kSolveLW; a.oh = kSolveLH; a.halo_x = 4; a.halo_y = 1;
     launch_solve_pass(h->stream, a, grad, 1, 1, g.h + 2);  // image rows + one apron row above and below
-    return check_launch(h, "solve_pass(resident)", 1);
+    return check_launch(h, FLOW2D_K_SOLVE_RESIDENT, 1);
   }
 
   int S = p->sweeps_per_pass;
@@ -299,13 +310,13 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
             a.halo_x = a.halo_y = s + 1;
             a.ow = a.oh = so;
             launch_solve_small_pass(h->stream, a, grad, (g.w + so - 1) / so, (vb - va + so - 1) / so);
-            TRY(check_launch(h, "solve_small_pass", 1));
+            TRY(check_launch(h, FLOW2D_K_SOLVE_SMALL_PASS, 1));
           }
         }
       }
       if (!small) {
         launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
-        TRY(check_launch(h, "solve_pass", 1));
+        TRY(check_launch(h, FLOW2D_K_SOLVE_PASS, 1));
       }
       cur_du = a.du_out; cur_dv = a.dv_out;
     }
@@ -319,11 +330,11 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
 
 int run_derivatives(flow2d_handle* h, const LevelGeom& g, const float* f0, const float* f1w) {
   launch_derivatives(h->stream, f0, f1w, h->c[C_FX], h->c[C_FY], h->c[C_FT], g);
-  TRY(check_launch(h, "derivatives", 1));
+  TRY(check_launch(h, FLOW2D_K_DERIVATIVES, 1));
   if (h->constancy == FLOW2D_GRADIENT) {
     float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
     launch_grad_tensor(h->stream, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, g);
-    TRY(check_launch(h, "grad_tensor", 1));
+    TRY(check_launch(h, FLOW2D_K_GRAD_TENSOR, 1));
   }
   return FLOW2D_OK;
 }
@@ -359,7 +370,7 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     TRY(gauss_taps(h, p->gaussian_sigma, &taps));
     for (int i = 0; i < 2; i++) {
       launch_blur(st, frame[i], h->c[C_BLUR0 + i], (int)W, (int)H, (int)h->pitch, taps);
-      TRY(check_launch(h, "blur", 1));
+      TRY(check_launch(h, FLOW2D_K_BLUR, 1));
       frame[i] = h->c[C_BLUR0 + i];
     }
   }
@@ -381,7 +392,7 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
       float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP1]};
       float* res[2] = {h->c[C_RES0], h->c[C_RES1]};
       launch_resample(st, frame, tmp, res, 2, (int)W, (int)H, g.w, g.h, g.pitch);
-      TRY(check_launch(h, "resample(frames)", 2));
+      TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
       fr[0] = res[0]; fr[1] = res[1];
     }
     // flow of this level: zero, or prolongated from the previous level (308-341)
@@ -393,12 +404,12 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
       float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP1]};
       float* out[2] = {u2, v2};
       launch_resample(st, in, tmp, out, 2, (int)pw, (int)ph, g.w, g.h, g.pitch);
-      TRY(check_launch(h, "resample(flow)", 2));
+      TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
       std::swap(u, u2); std::swap(v, v2);
     }
     // backward registration (344-363) and the level's derivative planes
     launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g);
-    TRY(check_launch(h, "warp", 1));
+    TRY(check_launch(h, FLOW2D_K_WARP, 1));
     TRY(run_derivatives(h, g, fr[0], h->c[C_WARPED]));
     // solve (366-406)
     TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], false, p, slab));
@@ -408,7 +419,7 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
       const float* b[2] = {h->c[C_DU0], h->c[C_DV0]};
       float* out[2] = {level == 0 ? out_u : u2, level == 0 ? out_v : v2};
       launch_add_median(st, a, b, out, 2, g.w, g.h, g.pitch, median);
-      TRY(check_launch(h, "add_median", 1));
+      TRY(check_launch(h, FLOW2D_K_ADD_MEDIAN, 1));
       std::swap(u, u2); std::swap(v, v2);
     }
     pw = cw; ph = ch;
@@ -453,6 +464,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   if (h->graph_exec && std::memcmp(&key, h->graph_key, sizeof key) == 0) {
     CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
     h->launches = h->graph_launches;
+    for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) h->kind_launches[k] = h->graph_kind_launches[k];
     h->levels_run = h->graph_levels;
     return FLOW2D_OK;
   }
@@ -464,7 +476,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
     (void)cudaGetLastError();
     return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);  // e.g. the stream is already capturing
   }
-  h->launches = 0;
+  reset_launch_counts(h);
   const int rc = enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
   cudaGraph_t graph = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
@@ -485,6 +497,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   static_assert(sizeof(GraphKey) <= sizeof(h->graph_key), "graph key storage too small");
   std::memcpy(h->graph_key, &key, sizeof key);
   h->graph_launches = h->launches;
+  for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) h->graph_kind_launches[k] = h->kind_launches[k];
   h->graph_levels = h->levels_run;
   CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
   return FLOW2D_OK;
@@ -582,6 +595,10 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
   h->constancy = constancy;
   const int ncont = constancy == FLOW2D_GRADIENT ? C_COUNT : C_J0;
   const size_t csize = h->pitch * height;
+  if (csize > (size_t)0x7fffffff) {  // kernels index a container with 32-bit offsets (25+ such containers exceed any HBM anyway)
+    delete h;
+    return FLOW2D_ERR_OUT_OF_MEMORY;
+  }
   if (cudaMalloc(&h->pool, csize * ncont * sizeof(float)) != cudaSuccess) {
     (void)cudaGetLastError();
     delete h;
@@ -634,6 +651,13 @@ int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launches, int* l
   return FLOW2D_OK;
 }
 
+int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts) {
+  if (!h || !counts) return FLOW2D_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) counts[k] = h->kind_launches[k];
+  return FLOW2D_OK;
+}
+const char* flow2d_kernel_kind_name(int kind) { return kind >= 0 && kind < FLOW2D_KERNEL_KINDS ? kKindNames[kind] : ""; }
+
 int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, float* d_flow_u,
                           float* d_flow_v, const flow2d_params* p) {
   if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
@@ -641,7 +665,7 @@ int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, const float*
   if (!aligned16(d_frame_0) || !aligned16(d_frame_1) || !aligned16(d_flow_u) || !aligned16(d_flow_v))
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "device containers must be 16-byte aligned");
   CU_TRY(h, cudaSetDevice(h->device));
-  h->launches = 0;
+  reset_launch_counts(h);
   return compute_on_device(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p);
 }
 
@@ -650,7 +674,7 @@ int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* fr
   if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
   if (!frame_0 || !frame_1 || !flow_u || !flow_v) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null image pointer");
   CU_TRY(h, cudaSetDevice(h->device));
-  h->launches = 0;
+  reset_launch_counts(h);
   const size_t row = h->W * sizeof(float), dpitch = h->pitch * sizeof(float);
   cudaStream_t st = h->stream;
   CU_TRY(h, cudaEventRecord(h->ev_start, st));
@@ -695,7 +719,7 @@ int flow2d_compute_slab_device(flow2d_handle* h, const float* d_frame_0, const f
   if (!slab || slab->world < 1 || slab->rank < 0 || slab->rank >= slab->world || (slab->world > 1 && !slab->exchange))
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "bad slab description");
   CU_TRY(h, cudaSetDevice(h->device));
-  h->launches = 0;
+  reset_launch_counts(h);
   return enqueue_pyramid(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p, slab);  // callbacks inside: no graph capture
 }
 
@@ -733,7 +757,7 @@ int flow2d_stage_blur(flow2d_handle* h, const float* d_in, float* d_out, size_t 
   GaussTaps taps;
   TRY(gauss_taps(h, sigma, &taps));
   launch_blur(h->stream, d_in, d_out, (int)w, (int)hh, (int)h->pitch, taps);
-  return check_launch(h, "blur", 1);
+  return check_launch(h, FLOW2D_K_BLUR, 1);
 }
 
 int flow2d_stage_resample(flow2d_handle* h, const float* d_in, size_t iw, size_t ih, float* d_out, size_t ow, size_t oh) {
@@ -745,7 +769,7 @@ int flow2d_stage_resample(flow2d_handle* h, const float* d_in, size_t iw, size_t
   float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP0]};
   float* out[2] = {d_out, d_out};
   launch_resample(h->stream, in, tmp, out, 1, (int)iw, (int)ih, (int)ow, (int)oh, (int)h->pitch);
-  return check_launch(h, "resample", 2);
+  return check_launch(h, FLOW2D_K_RESAMPLE, 2);
 }
 
 int flow2d_stage_warp(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, const float* d_flow_u,
@@ -755,7 +779,7 @@ int flow2d_stage_warp(flow2d_handle* h, const float* d_frame_0, const float* d_f
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "warp: bad buffers (in-place is refused)");
   TRY(check_level(h, w, hh));
   launch_warp(h->stream, d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_out, geom(h, w, hh, hx, hy));
-  return check_launch(h, "warp", 1);
+  return check_launch(h, FLOW2D_K_WARP, 1);
 }
 
 int flow2d_stage_solve(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, const float* d_flow_u,
@@ -783,7 +807,7 @@ int flow2d_stage_add(flow2d_handle* h, float* d_a, const float* d_b, size_t w, s
   if (!d_a || !d_b) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "add: null buffer");
   TRY(check_level(h, w, hh));
   launch_add(h->stream, d_a, d_b, (int)w, (int)hh, (int)h->pitch);
-  return check_launch(h, "add", 1);
+  return check_launch(h, FLOW2D_K_ADD, 1);
 }
 
 int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b, float* d_out, size_t w, size_t hh,
@@ -798,7 +822,7 @@ int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b
   const float* b[2] = {d_b, d_b};
   float* out[2] = {d_out, d_out};
   launch_add_median(h->stream, a, d_b ? b : nullptr, out, 1, (int)w, (int)hh, (int)h->pitch, r);
-  return check_launch(h, "add_median", 1);
+  return check_launch(h, FLOW2D_K_ADD_MEDIAN, 1);
 }
 
 int flow2d_stage_median(flow2d_handle* h, const float* d_in, float* d_out, size_t w, size_t hh, size_t radius) {

@@ -128,23 +128,36 @@ void launch_resample(cudaStream_t st, const float* const* in, float* const* tmp,
 // fma(w11,f11, fma(w01,f01, fma(f00,w00, w10*f10))).  Index work (floor, clamp, OOB/NaN test)
 // is bit exact by construction.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_pixel(const float* __restrict__ f0, const float* __restrict__ f1, float u, float v,
-                                            int xx, int yy, size_t c, int w, int h, int pitch, float rhx, float rhy,
+// Branch-free so that the 16 gathers of a thread's four pixels are all in flight at once: the taps of an
+// out-of-range pixel are clamped into the image (loaded, never used) and frame 0 is read under a predicate.
+struct WarpTap {
+  int i00, i01, i10, i11;  // element offsets of the four taps in frame 1
+  float w00, w10, w01, w11;
+  bool oob;
+};
+__device__ __forceinline__ WarpTap warp_tap(float u, float v, int xx, int yy, int w, int h, int pitch, float rhx, float rhy,
                                             float bx, float by) {
+  WarpTap t;
   const float x_f = fmaf(rhx, u, (float)xx);
   const float y_f = fmaf(rhy, v, (float)yy);
-  if ((x_f < 0.f) || (x_f > bx) || (y_f < 0.f) || (y_f > by) || isnan(x_f) || isnan(y_f)) return f0[c];
-  const int x = (int)floorf(x_f), y = (int)floorf(y_f);
-  const float dx = x_f - (float)x, dy = y_f - (float)y;
+  // (x_f < 0 || x_f > bx || y_f < 0 || y_f > by || isnan(x_f) || isnan(y_f)), registration_2d.cu:57
+  t.oob = !(x_f >= 0.f && x_f <= bx && y_f >= 0.f && y_f <= by);
+  const float xs = t.oob ? 0.f : x_f, ys = t.oob ? 0.f : y_f;
+  const int x = (int)xs, y = (int)ys;  // == floorf for the non-negative in-range values
+  const float dx = xs - (float)x, dy = ys - (float)y;
   const int x1 = min(w - 1, x + 1), y1 = min(h - 1, y + 1);
   const float ox = 1.f - dx, oy = 1.f - dy;
-  const float w00 = ox * oy, w10 = dx * oy, w01 = ox * dy, w11 = dx * dy;
-  const float* r0 = f1 + (size_t)y * pitch;
-  const float* r1 = f1 + (size_t)y1 * pitch;
-  float val = w10 * r0[x1];
-  val = fmaf(r0[x], w00, val);
-  val = fmaf(w01, r1[x], val);
-  return fmaf(w11, r1[x1], val);
+  t.w00 = ox * oy; t.w10 = dx * oy; t.w01 = ox * dy; t.w11 = dx * dy;
+  const int r0 = y * pitch, r1 = y1 * pitch;
+  t.i00 = r0 + x; t.i10 = r0 + x1; t.i01 = r1 + x; t.i11 = r1 + x1;
+  return t;
+}
+__device__ __forceinline__ float warp_blend(const WarpTap& t, float f00, float f10, float f01, float f11, float own) {
+  float val = t.w10 * f10;
+  val = fmaf(f00, t.w00, val);
+  val = fmaf(t.w01, f01, val);
+  val = fmaf(t.w11, f11, val);
+  return t.oob ? own : val;
 }
 
 // One thread = four consecutive pixels: float4 loads of u, v, one float4 store, 16 gathers in flight.
@@ -154,19 +167,28 @@ warp_kernel(const float* __restrict__ f0, const float* __restrict__ f1, const fl
   const int xx = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int yy = blockIdx.y * blockDim.y + threadIdx.y;
   if (xx >= w || yy >= h) return;
-  const size_t c = (size_t)yy * pitch + xx;
+  const int c = yy * pitch + xx;
   const float bx = (float)(w - 1), by = (float)(h - 1);
   if (xx + 3 < w) {
     const float4 uu = *reinterpret_cast<const float4*>(u + c), vv = *reinterpret_cast<const float4*>(v + c);
-    float4 o;
-    o.x = warp_pixel(f0, f1, uu.x, vv.x, xx, yy, c, w, h, pitch, rhx, rhy, bx, by);
-    o.y = warp_pixel(f0, f1, uu.y, vv.y, xx + 1, yy, c + 1, w, h, pitch, rhx, rhy, bx, by);
-    o.z = warp_pixel(f0, f1, uu.z, vv.z, xx + 2, yy, c + 2, w, h, pitch, rhx, rhy, bx, by);
-    o.w = warp_pixel(f0, f1, uu.w, vv.w, xx + 3, yy, c + 3, w, h, pitch, rhx, rhy, bx, by);
-    *reinterpret_cast<float4*>(out + c) = o;
+    const float us[4] = {uu.x, uu.y, uu.z, uu.w}, vs[4] = {vv.x, vv.y, vv.z, vv.w};
+    WarpTap t[4];
+    float f00[4], f10[4], f01[4], f11[4], own[4], o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) t[i] = warp_tap(us[i], vs[i], xx + i, yy, w, h, pitch, rhx, rhy, bx, by);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      f00[i] = f1[t[i].i00]; f10[i] = f1[t[i].i10]; f01[i] = f1[t[i].i01]; f11[i] = f1[t[i].i11];
+      own[i] = t[i].oob ? f0[c + i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = warp_blend(t[i], f00[i], f10[i], f01[i], f11[i], own[i]);
+    *reinterpret_cast<float4*>(out + c) = make_float4(o[0], o[1], o[2], o[3]);
   } else {
-    for (int i = 0; xx + i < w; i++)
-      out[c + i] = warp_pixel(f0, f1, u[c + i], v[c + i], xx + i, yy, c + i, w, h, pitch, rhx, rhy, bx, by);
+    for (int i = 0; xx + i < w; i++) {
+      const WarpTap t = warp_tap(u[c + i], v[c + i], xx + i, yy, w, h, pitch, rhx, rhy, bx, by);
+      out[c + i] = warp_blend(t, f1[t.i00], f1[t.i10], f1[t.i01], f1[t.i11], t.oob ? f0[c + i] : 0.f);
+    }
   }
 }
 

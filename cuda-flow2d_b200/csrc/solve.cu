@@ -65,19 +65,20 @@ __device__ __forceinline__ void unpack(const float4& q, float (&v)[4]) {
 }
 
 // Where this thread's strip lives in a global plane.  Cells outside the image are clamped to valid
-// memory; their values never reach a cell of the output tile.
+// memory; their values never reach a cell of the output tile.  Kept to two registers on purpose (the
+// rare scalar path recomputes its clamped columns): everything that stays live across the pass
+// competes with the sweep state for the 80 registers a thread may have.
 struct StripAddr {
-  size_t off;     // row * pitch + gx               (vector path)
-  size_t row;     // row * pitch                    (scalar path)
-  int cx[4];      // clamped columns                (scalar path)
+  int off;        // clamped row * pitch + gx  (a container has fewer than 2^31 elements: flow2d_create)
   bool interior;  // the strip lies completely inside [0, w)
 };
-__device__ __forceinline__ void load_strip(const float* __restrict__ p, const StripAddr& s, float (&v)[4]) {
+__device__ __forceinline__ void load_strip(const float* __restrict__ p, const StripAddr& s, int gx, int w, float (&v)[4]) {
   if (s.interior) {
     unpack(ld4(p + s.off), v);
   } else {
+    const float* row = p + (s.off - gx);
 #pragma unroll
-    for (int i = 0; i < 4; i++) v[i] = p[s.row + s.cx[i]];
+    for (int i = 0; i < 4; i++) v[i] = row[min(max(gx + i, 0), w - 1)];
   }
 }
 
@@ -189,11 +190,8 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   StripAddr sa;
   {
     const int my = min(max(gy, 0), h - 1);
-    sa.row = (size_t)my * pitch;
-    sa.off = sa.row + gx;
+    sa.off = my * pitch + gx;
     sa.interior = gx >= 0 && gx + 3 < w;
-#pragma unroll
-    for (int i = 0; i < 4; i++) sa.cx[i] = min(max(gx + i, 0), w - 1);
   }
 
   Strip t;
@@ -203,15 +201,15 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   // draining.  Everything the previous pass does not write (u, v, the derivative planes) is loaded
   // first; du, dv, phi, ksi only after griddepcontrol.wait (= previous grid complete and flushed).
   if (a.pdl) asm volatile("griddepcontrol.launch_dependents;");
-  load_strip(a.u, sa, t.uc);
-  load_strip(a.v, sa, t.vc);
-  load_strip(a.fx, sa, fx);
-  load_strip(a.fy, sa, fy);
-  load_strip(a.ft, sa, ft);
+  load_strip(a.u, sa, gx, w, t.uc);
+  load_strip(a.v, sa, gx, w, t.vc);
+  load_strip(a.fx, sa, gx, w, fx);
+  load_strip(a.fy, sa, gx, w, fy);
+  load_strip(a.ft, sa, gx, w, ft);
   if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (a.du_in) {
-    load_strip(a.du_in, sa, du);
-    load_strip(a.dv_in, sa, t.dv);
+    load_strip(a.du_in, sa, gx, w, du);
+    load_strip(a.dv_in, sa, gx, w, t.dv);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; i++) du[i] = t.dv[i] = 0.f;
@@ -224,20 +222,20 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   for (int outer = 0; outer < a.outer; ++outer) {
     // (the sweep loop of the previous outer iteration ended with a barrier: every plane is free)
     // resident mode: du of the previous outer iteration comes back from this thread's own store
-    if (outer > 0) load_strip(a.du_out, sa, du);
+    if (outer > 0) load_strip(a.du_out, sa, gx, w, du);
 
     // ------ phase A: remaining loads; motion tensor (solve_2d.cu:324-329 / 879-884); ksi (176-196) ------
     float phi[4];
     {
       float ksi[4];
       if (outer > 0) {
-        load_strip(a.fx, sa, fx);
-        load_strip(a.fy, sa, fy);
-        load_strip(a.ft, sa, ft);
+        load_strip(a.fx, sa, gx, w, fx);
+        load_strip(a.fy, sa, gx, w, fy);
+        load_strip(a.ft, sa, gx, w, ft);
       }
       if (a.phi_in) {
-        load_strip(a.phi_in, sa, phi);
-        load_strip(a.ksi_in, sa, ksi);
+        load_strip(a.phi_in, sa, gx, w, phi);
+        load_strip(a.ksi_in, sa, gx, w, ksi);
       }
       float J11[4], J22[4], J12[4], J13[4], J23[4];
 #pragma unroll
@@ -268,11 +266,11 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
       }
       st4(sm + P_KSI * PL + soff, ksi);
       if (GRAD) {
-        load_strip(a.J[0], sa, J11);
-        load_strip(a.J[1], sa, J22);
-        load_strip(a.J[2], sa, J12);
-        load_strip(a.J[3], sa, J13);
-        load_strip(a.J[4], sa, J23);
+        load_strip(a.J[0], sa, gx, w, J11);
+        load_strip(a.J[1], sa, gx, w, J22);
+        load_strip(a.J[2], sa, gx, w, J12);
+        load_strip(a.J[3], sa, gx, w, J13);
+        load_strip(a.J[4], sa, gx, w, J23);
       }
 #pragma unroll
       for (int i = 0; i < 4; i++) { J12[i] = -J12[i]; J13[i] = -J13[i]; J23[i] = -J23[i]; }

@@ -6,9 +6,10 @@
 // Outputs: <out><counter>flow-u-W-H.raw, flow-v-W-H.raw (float32), res.pgm (colour-coded flow, binary PPM),
 // amp-W-H.raw (float32 magnitude).
 // Exit codes: 0 ok / usage, 1 no CUDA device, 2 input files unreadable, 3 settings unreadable.
-//   cuda-flow2d --sequence <width> <height> <output path> <frame 0> <frame 1> ... <frame N>   (new)
+//   cuda-flow2d --sequence <width> <height> <output path> <frames...> | <directory> | <stack file> [options]   (new)
 //       flow between every pair of consecutive frames of a sequence, several pairs in flight at once
-//       (flow2d_compute_async on 4 handles); writes <out>NNNN_flow-u-W-H.raw / NNNN_flow-v-W-H.raw
+//       (host/sequence.h); 8-bit / float32 frames told apart by file size; writes
+//       <out>NNNN_flow-u-W-H.raw / NNNN_flow-v-W-H.raw (and NNNN_res.pgm / NNNN_amp-W-H.raw on request)
 // Differences: no getchar() at exit; the 8-bit reader is wired to Mode@imageType="8-bit";
 // files are also looked up under Input/Path@inputPath when they are not found in the CWD.
 #include <cmath>
@@ -21,55 +22,80 @@
 #include "flow2d.h"
 #include "io_utils.h"
 #include "optical_flow_2d.h"
+#include "sequence.h"
 #include "settings.h"
 
 using std::string;
 
 // Sequence mode: the X-ray-radiography use case of the reference README (one flow per consecutive
-// frame pair).  K handles, one stream each; pair i runs on handle i % K, and its result is written
-// while the other handles keep computing.
+// frame pair); host/sequence.{h,cpp} does the work.
 static int run_sequence(int argc, char** argv) {
-  if (argc < 7) {
-    std::cout << "Usage: " << argv[0] << " --sequence <width> <height> <output path> <frame 0> <frame 1> [...]" << std::endl;
-    return 0;
-  }
-  const size_t width = std::atoi(argv[2]), height = std::atoi(argv[3]);
-  const string out = argv[4];
-  const int n_frames = argc - 5, n_pairs = n_frames - 1;
-  const int K = n_pairs < 4 ? n_pairs : 4;
-  flow2d_params p;
-  flow2d_default_params(&p);  // src/main.cpp:70-80
-  p.throughput_mode = K > 1;
-  std::vector<flow2d_handle*> handles(K, nullptr);
-  for (int k = 0; k < K; k++)
-    if (flow2d_create(&handles[k], 0, width, height, FLOW2D_GREY) != FLOW2D_OK) return 1;
-  std::vector<Data2D> frames(n_frames);
-  for (int i = 0; i < n_frames; i++)
-    if (!frames[i].ReadRAWFromFileF32(argv[5 + i], width, height)) return 2;
-  std::vector<Data2D*> us(K), vs(K);
-  for (int k = 0; k < K; k++) { us[k] = new Data2D(width, height); vs[k] = new Data2D(width, height); }
-  const string suffix = "-" + std::to_string(width) + "-" + std::to_string(height) + ".raw";
-  auto flush = [&](int pair) {
-    const int k = pair % K;
-    flow2d_synchronize(handles[k]);
-    char tag[16];
-    std::snprintf(tag, sizeof tag, "%04d_", pair);
-    us[k]->WriteRAWToFileF32((out + tag + "flow-u" + suffix).c_str());
-    vs[k]->WriteRAWToFileF32((out + tag + "flow-v" + suffix).c_str());
-  };
-  int rc = 0;
-  for (int i = 0; i < n_pairs && rc == 0; i++) {
-    const int k = i % K;
-    if (i >= K) flush(i - K);  // the handle's previous pair must be on disk before its buffers are reused
-    if (flow2d_compute_async(handles[k], frames[i].DataPtr(), frames[i + 1].DataPtr(), us[k]->DataPtr(), vs[k]->DataPtr(), &p) !=
-        FLOW2D_OK) {
-      std::fprintf(stderr, "Error: %s\n", flow2d_last_error(handles[k]));
-      rc = 1;
+  FlowSequence::Options opt;
+  flow2d_default_params(&opt.params);  // src/main.cpp:70-80
+  FlowSequence::PixelType type = FlowSequence::PixelType::Auto;
+  bool list_only = false;
+  std::vector<string> pos;
+  for (int i = 2; i < argc; i++) {
+    const string a = argv[i];
+    if (a == "--handles" && i + 1 < argc) opt.handles = std::atoi(argv[++i]);
+    else if (a == "--device" && i + 1 < argc) opt.device = std::atoi(argv[++i]);
+    else if (a == "--u8") type = FlowSequence::PixelType::U8;
+    else if (a == "--f32") type = FlowSequence::PixelType::F32;
+    else if (a == "--color") opt.write_color = true;
+    else if (a == "--amp") opt.write_amp = true;
+    else if (a == "--no-flow") opt.write_flow = false;
+    else if (a == "--gradient") opt.constancy = FLOW2D_GRADIENT;
+    else if (a == "--list") list_only = true;
+    else if (a == "--settings" && i + 1 < argc) {
+      OpticFlow::Settings settings;  // solver values only; sizes and files come from the command line
+      if (settings.LoadSettings(argv[++i]) != 0) {
+        std::cout << settings.error << std::endl;
+        return 3;
+      }
+      opt.params.warp_levels_count = settings.levels;
+      opt.params.warp_scale_factor = settings.warpScale;
+      opt.params.outer_iterations_count = settings.iterOuter;
+      opt.params.inner_iterations_count = settings.iterInner;
+      opt.params.equation_alpha = settings.alpha;
+      opt.params.equation_data = settings.e_data;
+      opt.params.equation_smoothness = settings.e_smooth;
+      opt.params.median_radius = settings.medianRadius;
+      opt.params.gaussian_sigma = settings.sigma;
+      if (settings.constancy == "gradient") opt.constancy = FLOW2D_GRADIENT;
+    } else if (a.rfind("--", 0) == 0) {
+      std::cout << "Unknown option " << a << std::endl;
+      return 0;
+    } else {
+      pos.push_back(a);
     }
   }
-  for (int i = (n_pairs > K ? n_pairs - K : 0); i < n_pairs && rc == 0; i++) flush(i);
-  std::printf("Sequence: %d frame pairs of %zux%zu on %d concurrent handles\n", n_pairs, width, height, K);
-  for (int k = 0; k < K; k++) { delete us[k]; delete vs[k]; flow2d_destroy(handles[k]); }
+  if (pos.size() < 4) {
+    std::cout << "Usage: " << argv[0] << " --sequence <width> <height> <output path> <frame 0> <frame 1> [...] | <directory> | <stack file>\n"
+              << "       [--handles K] [--u8|--f32] [--settings file] [--gradient] [--color] [--amp] [--no-flow] [--device D] [--list]"
+              << std::endl;
+    return 0;
+  }
+  const size_t width = std::atoi(pos[0].c_str()), height = std::atoi(pos[1].c_str());
+  const string out = pos[2];
+  FlowSequence::FrameSource source;
+  if (!source.Open(std::vector<string>(pos.begin() + 3, pos.end()), width, height, type) || source.Count() < 2) {
+    std::cout << (source.error.empty() ? string("a sequence needs two or more frames") : source.error) << std::endl;
+    return 2;
+  }
+  std::printf("Sequence: %d frames of %zux%zu (%s, %s)\n", source.Count(), width, height, source.Kind(),
+              source.Type() == FlowSequence::PixelType::U8 ? "8-bit" : "float32");
+  if (list_only) {
+    for (int i = 0; i < source.Count(); i++) std::printf("  %04d %s\n", i, source.Name(i).c_str());
+    return 0;
+  }
+  FlowSequence::Stats st;
+  const int rc = FlowSequence::Run(source, out, opt, &st);
+  if (rc == 0) {
+    std::printf("Sequence: %d frame pairs on %d concurrent handles in %.3f s: %.2f pairs/s, %.2f Mpix/s end to end\n", st.pairs,
+                st.handles, st.seconds, st.pairs / st.seconds, st.pairs * (double)width * height / st.seconds * 1e-6);
+    std::printf("Sequence: reader busy %.3f s, writer busy %.3f s; scheduler waited %.3f s for frames, %.3f s for the GPU, %.3f s for the writer\n",
+                st.read_seconds, st.write_seconds, st.wait_frames_seconds, st.wait_gpu_seconds, st.wait_writer_seconds);
+  }
   return rc;
 }
 

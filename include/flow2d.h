@@ -114,6 +114,16 @@ FLOW2D_API int flow2d_synchronize(flow2d_handle* h);
  * of the reference's "Total GPU computation time" (optical_flow_2d.cpp:179,548-554). */
 FLOW2D_API int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launches, int* levels_run, float* device_ms);
 
+/* The same launch count split by kernel (index = FLOW2D_K_*), e.g. to name the dominant kernel of a
+ * workload.  No reference counterpart (the reference launches blindly, cuda_operation_*.cpp). */
+enum {
+  FLOW2D_K_BLUR = 0, FLOW2D_K_RESAMPLE, FLOW2D_K_WARP, FLOW2D_K_DERIVATIVES, FLOW2D_K_GRAD_TENSOR, FLOW2D_K_SOLVE_PASS,
+  FLOW2D_K_SOLVE_RESIDENT, FLOW2D_K_SOLVE_SMALL_PASS, FLOW2D_K_SOLVE_TINY, FLOW2D_K_ADD_MEDIAN, FLOW2D_K_ADD,
+  FLOW2D_KERNEL_KINDS
+};
+FLOW2D_API int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts /* [FLOW2D_KERNEL_KINDS] */);
+FLOW2D_API const char* flow2d_kernel_kind_name(int kind);
+
 /* ---- level table: replaces OpticalFlowBase2D::GetMaxWarpLevel and the per-level size formulas ---
  * (src/optical_flow/optical_flow_base_2d.cpp:36-59, src/optical_flow/optical_flow_2d.cpp:268-272).
  * Host-only integer/fp32 arithmetic, bit-exact with the reference. */

@@ -87,3 +87,75 @@ def test_sequence_mode_equals_pairwise(synth, oracle, tmp_path):
         v = np.fromfile(tmp_path / "out" / ("%04d_flow-v-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
         ou, ov = oracle.compute_flow(frames[i], frames[i + 1], p)
         assert np.all(u == ou) and np.all(v == ov), "pair %d" % i
+
+
+def test_sequence_stack_u8_directory_and_writers(rub, oracle, tmp_path):
+    """--sequence on an 8-bit multi-frame stack and on a directory of float32 frames (frame source auto-detection,
+    reader / writer threads, 2K output slots): every pair equals the oracle bit for bit; --color / --amp write the
+    same res.pgm / amp files as the single-pair command line does for that pair."""
+    w, h, n = 72, 56, 11
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 255, (h + 2 * n, w + 2 * n), dtype=np.uint8)
+    k = np.ones(5) / 5.0
+    smooth = np.apply_along_axis(lambda r: np.convolve(r, k, "same"), 1, base.astype(np.float64))
+    smooth = np.apply_along_axis(lambda c: np.convolve(c, k, "same"), 0, smooth)
+    frames = [np.ascontiguousarray(smooth[i:i + h, n - i:n - i + w]).astype(np.uint8) for i in range(n)]  # a moving window
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    (tmp_path / "one").mkdir()
+    (tmp_path / "dir").mkdir()
+    np.stack(frames).tofile(tmp_path / "stack.raw")
+    for i, f in enumerate(frames):
+        f.astype(np.float32).tofile(tmp_path / "dir" / ("frame%03d.raw" % i))
+    r = _run(CLI, ["--sequence", w, h, "a/", "stack.raw", "--handles", 3, "--color", "--amp"], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    assert b"11 frames of 72x56 (stack, 8-bit)" in r.stdout and b"10 frame pairs on 3 concurrent handles" in r.stdout
+    r = _run(CLI, ["--sequence", w, h, "b/", "dir", "--handles", 8], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    assert b"(directory, float32)" in r.stdout
+    p = oracle.make_params()
+    for i in range(n - 1):
+        ou, ov = oracle.compute_flow(frames[i].astype(np.float32), frames[i + 1].astype(np.float32), p)
+        for d in ("a", "b"):
+            u = np.fromfile(tmp_path / d / ("%04d_flow-u-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+            v = np.fromfile(tmp_path / d / ("%04d_flow-v-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+            assert np.all(u == ou) and np.all(v == ov), "pair %d (%s)" % (i, d)
+    # writers: pair 4 through the single-pair command line
+    r = _run(CLI, ["dir/frame004.raw", "dir/frame005.raw", w, h, "p4_", "one/"], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    for seq_name, one_name in (("0004_res.pgm", "p4_res.pgm"), ("0004_amp-%d-%d.raw" % (w, h), "p4_amp-%d-%d.raw" % (w, h))):
+        assert (tmp_path / "a" / seq_name).read_bytes() == (tmp_path / "one" / one_name).read_bytes(), seq_name
+
+
+def test_sequence_gradient_settings_and_read_failure(synth, oracle, tmp_path):
+    """--settings takes the solver values of a settings.xml, --gradient the data term; a frame that disappears
+    mid-sequence ends the run with exit code 2 without hanging the pipeline."""
+    w, h, n = 64, 48, 5
+    (tmp_path / "out").mkdir()
+    frames = []
+    for i in range(n):
+        f, _, _, _ = synth.make_pair(w, h, 7, U0=(0.3 * i, 0.1 * i), U1=0.0)
+        frames.append(f)
+        f.tofile(tmp_path / ("s%02d.raw" % i))
+    (tmp_path / "s.xml").write_text(
+        '<Settings><Input><Path inputPath="./"/><Mode Nx="1" Ny="1" imageType="32-bit"><Files file1="x" file2="y"/></Mode></Input>'
+        '<Parameters><Method key="false"/><Solver><Iterations inner="3" outer="4"/>'
+        '<Warping levels="6" scaling="0.8" medianRadius="3"/><Model sigma="0.8" alpha="12" e_smooth="0.01" e_data="0.02"/></Solver>'
+        '</Parameters>'
+        '<Output><Path outputPath="./"/></Output></Settings>')
+    names = ["s%02d.raw" % i for i in range(n)]
+    r = _run(CLI, ["--sequence", w, h, "out/", "--settings", "s.xml", "--gradient"] + names, tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    p = oracle.make_params(levels=6, scale=0.8, outer=4, inner=3, alpha=12.0, e_smooth=0.01, e_data=0.02, median=3, sigma=0.8,
+                           constancy=oracle.GRADIENT)
+    for i in range(n - 1):
+        u = np.fromfile(tmp_path / "out" / ("%04d_flow-u-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+        v = np.fromfile(tmp_path / "out" / ("%04d_flow-v-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+        ou, ov = oracle.compute_flow(frames[i], frames[i + 1], p)
+        assert np.all(u == ou) and np.all(v == ov), "pair %d" % i
+    # a truncated frame in the middle of a stack of files is caught by the size check up front ...
+    (tmp_path / "s02.raw").write_bytes(b"1234")
+    assert _run(CLI, ["--sequence", w, h, "out/"] + names, tmp_path).returncode == 2
+    # ... an output directory that does not exist by the writer thread (exit code 4)
+    frames[2].tofile(tmp_path / "s02.raw")
+    assert _run(CLI, ["--sequence", w, h, "missing_dir/"] + names, tmp_path).returncode == 4

@@ -8,7 +8,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem --format=csv > $OUT/gpu.txt
 nproc >> $OUT/gpu.txt; lscpu | grep "Model name" >> $OUT/gpu.txt
 python -m pytest tests -m gpu -q 2>&1 | tail -5 > $OUT/pytest.log; tail -2 $OUT/pytest.log
-for wl in c2 c1b c4 c3; do
+for wl in c2 rub_c1b rub_c1a c1b c4 c3; do
   python bench.py --impl reference --workload $wl --steps 3 --warmup 1 2>&1 | tail -1 > $OUT/bench_ref_$wl.json
   python bench.py --workload $wl --steps 10 --warmup 3 2>&1 | tail -1 > $OUT/bench_$wl.json
   python - <<PY
@@ -24,7 +24,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 78 -c 78 --csv --lo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches_c1b.csv python tools/profile_step.py c1b 0 1 > $OUT/ncu_c1b.log 2>&1
 # full captures of the dominant kernel: C2 later pass (L2-resident), C3 finest level (DRAM-resident), one tiny level
 ncu --set full --clock-control none --import-source on -k regex:solve_pass -s 40 -c 1 -o $OUT/solve_c2 python tools/profile_step.py c2 0 1 > $OUT/ncu_full_c2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:solve_pass -s 1180 -c 1 -o $OUT/solve_c3 python tools/profile_step.py c3 0 1 > $OUT/ncu_full_c3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:solve_pass -s 3 -c 1 -o $OUT/solve_c3 python tools/profile_stages.py 4096 4096 > $OUT/ncu_full_c3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:solve_tiny -s 12 -c 1 -o $OUT/solve_tiny python tools/profile_step.py c1b 0 1 > $OUT/ncu_full_tiny.log 2>&1
 # per-kernel DRAM traffic and time at 4096x4096
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $OUT/stages_4096.csv python tools/profile_stages.py 4096 4096 > $OUT/stages.log 2>&1
