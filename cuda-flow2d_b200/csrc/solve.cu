@@ -33,6 +33,8 @@
 //
 // "Resident" mode: if the whole level fits one region, a single CTA runs ALL outer iterations and
 // all inner sweeps of the level without leaving the SM (grid = 1).
+#include <type_traits>
+
 #include "kernels.h"
 
 namespace flow2d {
@@ -51,7 +53,8 @@ enum {
   // phase B planes, aliased onto planes that are first written after the barrier ending phase B
   P_U = P_EYP, P_V = P_EYM, P_DU = P_DENU, P_DV = P_DENV,
   P_PHI = P_SU1,                    // read in phase C; sweep 1 is the first writer of SU1
-  P_J11 = P_RU, P_J22 = P_RV        // thread-private hand-over A -> C
+  P_J11 = P_RU, P_J22 = P_RV,       // thread-private hand-over A -> C (gradient constancy: the loaded tensor)
+  P_FX = P_RU, P_FY = P_RV, P_FT = P_NJ12  // same for brightness constancy: fx, fy, ft
 };
 
 size_t solve_pass_smem_bytes() { return sizeof(float) * PL * kNumPlanes; }
@@ -63,6 +66,31 @@ __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
 __device__ __forceinline__ void unpack(const float4& q, float (&v)[4]) {
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
 }
+
+// Shared-memory access of the pass: every plane is a compile-time byte offset from ONE per-thread
+// address register (this strip in plane 0), the rows above / below from two more.  Written as PTX
+// so that the 32-bit shared address stays in a register: with the generic `sm + plane * PL + soff`
+// form the compiler, short of registers, re-derived the address from %tid and the shared window
+// base (S2R, S2UR, ~30 integer instructions) in every sweep.
+template <int PLANE>
+__device__ __forceinline__ void lds4(unsigned addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %5];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+               : "r"(addr), "n"(PLANE * PL * 4)
+               : "memory");
+}
+template <int PLANE>
+__device__ __forceinline__ void sts4(unsigned addr, const float (&v)[4]) {
+  asm volatile("st.shared.v4.f32 [%0 + %1], {%2, %3, %4, %5};" ::"r"(addr), "n"(PLANE * PL * 4), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3])
+               : "memory");
+}
+
+// A value the register allocator must KEEP rather than re-derive: passing it through a shuffle with
+// the own lane as source makes it opaque to rematerialisation (one SHFL, once per pass).
+__device__ __forceinline__ unsigned keep(unsigned x) { return __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
+__device__ __forceinline__ int keep(int x) { return __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
+__device__ __forceinline__ float keep(float x) { return __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
 
 // Where this thread's strip lives in a global plane.  Cells outside the image are clamped to valid
 // memory; their values never reach a cell of the output tile.  Kept to two registers on purpose (the
@@ -160,10 +188,10 @@ __device__ __forceinline__ void stamp(const SolveArgs& a, int slot) {
   }
 }
 
-template <bool GRAD, bool BORDER>
+template <bool GRAD, bool BORDER, bool TIMING>
 __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   const int tid = threadIdx.x;
-  stamp(a, 0);
+  if (TIMING) stamp(a, 0);
   const int row = tid >> 4;       // row of the region
   const int lx = 4 * (tid & 15);  // first column of the strip within the region
   const int w = a.w, h = a.h, pitch = a.pitch;
@@ -172,7 +200,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   const int ox1 = min(w, ox0 + a.ow), oy1 = min(a.y1, oy0 + a.oh);
   const int gx = ox0 - a.halo_x + lx;  // multiple of 4
   const int gy = oy0 - a.halo_y + row;
-  const int soff = row * LW + lx;
+  const unsigned sb = (unsigned)__cvta_generic_to_shared(sm) + 4u * (unsigned)(row * LW + lx);  // this strip, plane 0
   const int last_row = (int)(blockDim.x >> 4) - 1;  // LH-1, or fewer rows for a small resident level
   // Neighbour rows.  Image border: the mirrored neighbour is the opposite neighbour.  The first and
   // last row of the region have no neighbour row in shared memory (they are never exact anyway).
@@ -181,6 +209,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
     if (gy == 0 && row < last_row) up_off = LW;
     if (gy == h - 1 && row > 0) dn_off = -LW;
   }
+  const unsigned sb_up = sb + 4 * up_off, sb_dn = sb + 4 * dn_off;
   const bool x_lo = BORDER && gx == 0;        // only element 0 of a strip can be x == 0 (gx % 4 == 0)
   const int i_hi = BORDER ? w - 1 - gx : -1;  // element index of x == w-1 in this strip, if 0..3
   bool inside[4];                             // cells outside the image exist only in BORDER CTAs
@@ -191,7 +220,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
   {
     const int my = min(max(gy, 0), h - 1);
     sa.off = my * pitch + gx;
-    sa.interior = gx >= 0 && gx + 3 < w;
+    sa.interior = !BORDER || (gx >= 0 && gx + 3 < w);  // an interior region has no partial strip
   }
 
   Strip t;
@@ -215,9 +244,6 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
     for (int i = 0; i < 4; i++) du[i] = t.dv[i] = 0.f;
   }
 
-  const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
-  const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
-  const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
 
   for (int outer = 0; outer < a.outer; ++outer) {
     // (the sweep loop of the previous outer iteration ended with a barrier: every plane is free)
@@ -264,49 +290,57 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
 #pragma unroll
         for (int i = 0; i < 4; i++) ksi[i] = inside[i] ? ksi[i] : 0.f;
       }
-      st4(sm + P_KSI * PL + soff, ksi);
+      sts4<P_KSI>(sb, ksi);
       if (GRAD) {
         load_strip(a.J[0], sa, gx, w, J11);
         load_strip(a.J[1], sa, gx, w, J22);
         load_strip(a.J[2], sa, gx, w, J12);
         load_strip(a.J[3], sa, gx, w, J13);
         load_strip(a.J[4], sa, gx, w, J23);
-      }
 #pragma unroll
-      for (int i = 0; i < 4; i++) { J12[i] = -J12[i]; J13[i] = -J13[i]; J23[i] = -J23[i]; }
-      st4(sm + P_J11 * PL + soff, J11);
-      st4(sm + P_J22 * PL + soff, J22);
-      st4(sm + P_NJ12 * PL + soff, J12);
-      st4(sm + P_NJ13 * PL + soff, J13);
-      st4(sm + P_NJ23 * PL + soff, J23);
+        for (int i = 0; i < 4; i++) { J12[i] = -J12[i]; J13[i] = -J13[i]; J23[i] = -J23[i]; }
+        sts4<P_J11>(sb, J11);
+        sts4<P_J22>(sb, J22);
+        sts4<P_NJ12>(sb, J12);
+        sts4<P_NJ13>(sb, J13);
+        sts4<P_NJ23>(sb, J23);
+      } else {
+        // brightness constancy: the tensor is five products of fx, fy, ft; three planes are handed to
+        // phase C instead of five, and the products need not stay live next to the ksi arithmetic
+        sts4<P_FX>(sb, fx);
+        sts4<P_FY>(sb, fy);
+        sts4<P_FT>(sb, ft);
+      }
     }
 
-    stamp(a, 1);
+    if (TIMING) stamp(a, 1);
     if (!a.phi_in) {
       // ---------------- phase B: phi (solve_2d.cu:141-162) ----------------
-      st4(sm + P_U * PL + soff, t.uc);
-      st4(sm + P_V * PL + soff, t.vc);
-      st4(sm + P_DU * PL + soff, du);
-      st4(sm + P_DV * PL + soff, t.dv);
+      sts4<P_U>(sb, t.uc);
+      sts4<P_V>(sb, t.vc);
+      sts4<P_DU>(sb, du);
+      sts4<P_DV>(sb, t.dv);
       __syncthreads();
       float dux[4], duy[4], dvx[4], dvy[4], num[4];
+      const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
+      const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
       {
         float nU[4], nD[4];
-        unpack(ld4(sm + P_U * PL + soff + up_off), nU);
-        unpack(ld4(sm + P_U * PL + soff + dn_off), nD);
+        lds4<P_U>(sb_up, nU);
+        lds4<P_U>(sb_dn, nD);
 #pragma unroll
         for (int i = 0; i < 4; i++) num[i] = nD[i] - nU[i];
-        unpack(ld4(sm + P_DU * PL + soff + up_off), nU);
-        unpack(ld4(sm + P_DU * PL + soff + dn_off), nD);
+        lds4<P_DU>(sb_up, nU);
+        lds4<P_DU>(sb_dn, nD);
 #pragma unroll
         for (int i = 0; i < 4; i++) num[i] = (num[i] + nD[i]) - nU[i];
         div_rn4(num, hy2, rhy2, duy);
-        unpack(ld4(sm + P_V * PL + soff + up_off), nU);
-        unpack(ld4(sm + P_V * PL + soff + dn_off), nD);
+        lds4<P_V>(sb_up, nU);
+        lds4<P_V>(sb_dn, nD);
 #pragma unroll
         for (int i = 0; i < 4; i++) num[i] = nD[i] - nU[i];
-        unpack(ld4(sm + P_DV * PL + soff + up_off), nU);
-        unpack(ld4(sm + P_DV * PL + soff + dn_off), nD);
+        lds4<P_DV>(sb_up, nU);
+        lds4<P_DV>(sb_dn, nD);
 #pragma unroll
         for (int i = 0; i < 4; i++) num[i] = (num[i] + nD[i]) - nU[i];
         div_rn4(num, hy2, rhy2, dvy);
@@ -346,19 +380,37 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         phi[i] = 1.f / (r + r);
       }
     }
-    st4(sm + P_PHI * PL + soff, phi);
+    sts4<P_PHI>(sb, phi);
     __syncthreads();  // phi published; every reader of P_U..P_DV is done, so their aliases are free
-    stamp(a, 2);
+    if (TIMING) stamp(a, 2);
 
     // ---------------- phase C: weights and denominators (solve_2d.cu:333-349, 363, 367) ----------------
     {
       const float pL = __shfl_up_sync(0xffffffffu, phi[3], 1), pR = __shfl_down_sync(0xffffffffu, phi[0], 1);
       float pU[4], pD[4], J11[4], J22[4], ksi[4];
-      unpack(ld4(sm + P_PHI * PL + soff + up_off), pU);
-      unpack(ld4(sm + P_PHI * PL + soff + dn_off), pD);
-      unpack(ld4(sm + P_J11 * PL + soff), J11);
-      unpack(ld4(sm + P_J22 * PL + soff), J22);
-      unpack(ld4(sm + P_KSI * PL + soff), ksi);
+      lds4<P_PHI>(sb_up, pU);
+      lds4<P_PHI>(sb_dn, pD);
+      lds4<P_KSI>(sb, ksi);
+      if (GRAD) {
+        lds4<P_J11>(sb, J11);
+        lds4<P_J22>(sb, J22);
+        lds4<P_NJ12>(sb, t.nJ12);
+      } else {
+        float gfx[4], gfy[4], gft[4], nJ13[4], nJ23[4];
+        lds4<P_FX>(sb, gfx);
+        lds4<P_FY>(sb, gfy);
+        lds4<P_FT>(sb, gft);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          J11[i] = gfx[i] * gfx[i];
+          J22[i] = gfy[i] * gfy[i];
+          t.nJ12[i] = -(gfx[i] * gfy[i]);
+          nJ13[i] = -(gfx[i] * gft[i]);
+          nJ23[i] = -(gfy[i] * gft[i]);
+        }
+        sts4<P_NJ13>(sb, nJ13);
+        sts4<P_NJ23>(sb, nJ23);
+      }
       if (a.phi_out && !a.phi_in) {  // a later pass of this outer iteration reloads the robust weights
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -369,6 +421,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
           }
         }
       }
+      const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
       // Neumann boundary through zero weights (solve_2d.cu:337-340)
       float wyp = hy_2, wym = hy_2;
       if (BORDER) {
@@ -409,39 +462,41 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         t.su[i] = t.uc[i] + du[i];
         t.sv[i] = t.vc[i] + t.dv[i];
       }
-      st4(sm + P_EYP * PL + soff, eyp);
-      st4(sm + P_EYM * PL + soff, eym);
-      st4(sm + P_DENU * PL + soff, denU);
-      st4(sm + P_DENV * PL + soff, denV);
-      st4(sm + P_RU * PL + soff, rU);
-      st4(sm + P_RV * PL + soff, rV);
-      st4(sm + P_SU0 * PL + soff, t.su);
-      st4(sm + P_SV0 * PL + soff, t.sv);
-      unpack(ld4(sm + P_NJ12 * PL + soff), t.nJ12);
+      // (the compiler would otherwise keep phi and rebuild the three inner x weights in every sweep)
+#pragma unroll
+      for (int i = 1; i < 4; i++) t.ex[i] = keep(t.ex[i]);
+      sts4<P_EYP>(sb, eyp);
+      sts4<P_EYM>(sb, eym);
+      sts4<P_DENU>(sb, denU);
+      sts4<P_DENV>(sb, denV);
+      sts4<P_RU>(sb, rU);
+      sts4<P_RV>(sb, rV);
+      sts4<P_SU0>(sb, t.su);
+      sts4<P_SV0>(sb, t.sv);
     }
     __syncthreads();
-    stamp(a, 3);
+    if (TIMING) stamp(a, 3);
 
     // ---------------- phase D: Jacobi sweeps (solve_2d.cu:350-367 as compiled) ----------------
-    for (int k = 1; k <= a.sweeps; ++k) {
-      // Rows further than sweeps-k from the output tile can no longer influence it: whole warps
-      // (two rows) outside that window skip the sweep (nothing reads what they would write).
-      const int grow = a.sweeps - k;
-      if (!__any_sync(0xffffffffu, gy >= oy0 - grow && gy < oy1 + grow)) {
+    // Rows further than sweeps-k from the output tile can no longer influence it: whole warps (two
+    // rows) outside that window skip the sweep (nothing reads what they would write).
+    const int need = keep(max(oy0 - gy, gy - oy1 + 1));  // this row matters as long as sweeps-k >= need
+    // one sweep; ODD = the sweep number is odd: reads s_u/s_v buffer 0, writes buffer 1
+    const unsigned kb = keep(sb), kb_up = keep(sb_up), kb_dn = keep(sb_dn);  // address registers of the sweeps
+    auto sweep = [&](auto odd, int k) {
+      constexpr bool ODD = decltype(odd)::value;
+      constexpr int CU = ODD ? P_SU0 : P_SU1, CV = ODD ? P_SV0 : P_SV1, NU = ODD ? P_SU1 : P_SU0, NV = ODD ? P_SV1 : P_SV0;
+      if (!__any_sync(0xffffffffu, a.sweeps - k >= need)) {
         __syncthreads();
-        continue;
+        return;
       }
-      const float* cur_u = sm + ((k & 1) ? P_SU0 : P_SU1) * PL + soff;
-      const float* cur_v = sm + ((k & 1) ? P_SV0 : P_SV1) * PL + soff;
-      float* nxt_u = sm + ((k & 1) ? P_SU1 : P_SU0) * PL + soff;
-      float* nxt_v = sm + ((k & 1) ? P_SV1 : P_SV0) * PL + soff;
       const float suL = __shfl_up_sync(0xffffffffu, t.su[3], 1), suR = __shfl_down_sync(0xffffffffu, t.su[0], 1);
       const float svL = __shfl_up_sync(0xffffffffu, t.sv[3], 1), svR = __shfl_down_sync(0xffffffffu, t.sv[0], 1);
       float nU[4], nD[4], eyp[4], eym[4], sumU[4], sumV[4];
-      unpack(ld4(sm + P_EYP * PL + soff), eyp);
-      unpack(ld4(sm + P_EYM * PL + soff), eym);
-      unpack(ld4(cur_u + up_off), nU);
-      unpack(ld4(cur_u + dn_off), nD);
+      lds4<P_EYP>(kb, eyp);
+      lds4<P_EYM>(kb, eym);
+      lds4<CU>(kb_up, nU);
+      lds4<CU>(kb_dn, nD);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         float l, r;
@@ -453,8 +508,8 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         s = fmaf(eyp[i], nD[i] - u0, s);
         sumU[i] = fmaf(eym[i], nU[i] - u0, s);
       }
-      unpack(ld4(cur_v + up_off), nU);
-      unpack(ld4(cur_v + dn_off), nD);
+      lds4<CV>(kb_up, nU);
+      lds4<CV>(kb_dn, nD);
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         float l, r;
@@ -469,15 +524,15 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
       float nj[4], den[4], rcp[4], num[4], rdv[4];
       const float (&ksi)[4] = t.ksi;
       const float (&nJ12)[4] = t.nJ12;
-      unpack(ld4(sm + P_NJ13 * PL + soff), nj);
-      unpack(ld4(sm + P_DENU * PL + soff), den);
-      unpack(ld4(sm + P_RU * PL + soff), rcp);
+      lds4<P_NJ13>(kb, nj);
+      lds4<P_DENU>(kb, den);
+      lds4<P_RU>(kb, rcp);
 #pragma unroll
       for (int i = 0; i < 4; i++) num[i] = fmaf(ksi[i], fmaf(nJ12[i], t.dv[i], nj[i]), sumU[i]);
       div_rn4(num, den, rcp, t.den_ok, du);
-      unpack(ld4(sm + P_NJ23 * PL + soff), nj);
-      unpack(ld4(sm + P_DENV * PL + soff), den);
-      unpack(ld4(sm + P_RV * PL + soff), rcp);
+      lds4<P_NJ23>(kb, nj);
+      lds4<P_DENV>(kb, den);
+      lds4<P_RV>(kb, rcp);
 #pragma unroll
       for (int i = 0; i < 4; i++) num[i] = fmaf(ksi[i], fmaf(nJ12[i], du[i], nj[i]), sumV[i]);
       div_rn4(num, den, rcp, t.den_ok, rdv);
@@ -487,12 +542,16 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         t.su[i] = t.uc[i] + du[i];
         t.sv[i] = t.vc[i] + rdv[i];
       }
-      st4(nxt_u, t.su);
-      st4(nxt_v, t.sv);
+      sts4<NU>(kb, t.su);
+      sts4<NV>(kb, t.sv);
       __syncthreads();
+    };
+    for (int k = 1; k <= a.sweeps; k += 2) {
+      sweep(std::true_type{}, k);
+      if (k + 1 <= a.sweeps) sweep(std::false_type{}, k + 1);
     }
 
-    stamp(a, 4);
+    if (TIMING) stamp(a, 4);
     // ---------------- phase E: store du, dv of the output tile ----------------
     if (gy >= oy0 && gy < oy1) {
       float* rdu = a.du_out + (size_t)gy * pitch;
@@ -508,26 +567,29 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         }
       }
     }
-    stamp(a, 5);
+    if (TIMING) stamp(a, 5);
   }
 }
 
-template <bool GRAD>
+// TIMING: the variant with the %globaltimer stamps of flow2d_debug_timing (tools/phase_timing.py); the
+// production kernel carries neither the stamps nor the registers of their address arithmetic.
+template <bool GRAD, bool TIMING>
 __global__ void __launch_bounds__(NT, 1) solve_pass_kernel(const SolveArgs a) {
   extern __shared__ __align__(16) float sm[];
   // does this CTA's region reach the image border (or beyond)?
   const int lx0 = blockIdx.x * a.ow - a.halo_x, ly0 = a.y0 + blockIdx.y * a.oh - a.halo_y;
   const bool border = lx0 <= 0 || lx0 + LW >= a.w || ly0 <= 0 || ly0 + (int)(blockDim.x >> 4) >= a.h;
-  if (border) pass_body<GRAD, true>(a, sm);
-  else pass_body<GRAD, false>(a, sm);
+  if (border) pass_body<GRAD, true, TIMING>(a, sm);
+  else pass_body<GRAD, false, TIMING>(a, sm);
 }
 
 cudaError_t solve_pass_configure() {
-  cudaError_t e = cudaFuncSetAttribute(solve_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)solve_pass_smem_bytes());
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(solve_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)solve_pass_smem_bytes());
+  const int bytes = (int)solve_pass_smem_bytes();
+  cudaError_t e = cudaFuncSetAttribute(solve_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e;
 }
 
 void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows) {
@@ -543,8 +605,13 @@ void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = a.pdl ? 1 : 0;  // only between consecutive passes of one solve (see SolveArgs::pdl)
-  if (grad) cudaLaunchKernelEx(&cfg, solve_pass_kernel<true>, a);
-  else cudaLaunchKernelEx(&cfg, solve_pass_kernel<false>, a);
+  if (a.timing) {
+    if (grad) cudaLaunchKernelEx(&cfg, solve_pass_kernel<true, true>, a);
+    else cudaLaunchKernelEx(&cfg, solve_pass_kernel<false, true>, a);
+  } else {
+    if (grad) cudaLaunchKernelEx(&cfg, solve_pass_kernel<true, false>, a);
+    else cudaLaunchKernelEx(&cfg, solve_pass_kernel<false, false>, a);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
