@@ -110,6 +110,25 @@ __device__ __forceinline__ void load_strip(const float* __restrict__ p, const St
   }
 }
 
+// Global -> shared without a register in between (LDGSTS).  Planes that a phase only needs in shared
+// memory anyway (hand-over and published planes) are staged this way: a register load followed by a
+// store would hold four registers per plane across the whole load latency, and with nine planes in
+// flight the compiler spilled freshly loaded values, i.e. waited for each load in turn.
+__device__ __forceinline__ void cp_async16(unsigned dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int PLANE>
+__device__ __forceinline__ void stage_strip(const float* __restrict__ p, const StripAddr& s, int gx, int w, unsigned sb) {
+  if (s.interior) {
+    cp_async16(sb + PLANE * PL * 4, p + s.off);
+  } else {
+    float v[4];
+    load_strip(p, s, gx, w, v);
+    sts4<PLANE>(sb, v);
+  }
+}
+
 // ---- IEEE division by a divisor that is reused many times ------------------------------------
 // div.rn.f32 is implemented by the hardware as
 //     r0 = MUFU.RCP(d); e = fma(-d, r0, 1); r = fma(r0, e, r0);        (refined reciprocal)
@@ -225,102 +244,96 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
 
   Strip t;
   float du[4];  // increment in u: live in phases A-C and as the sweeps' result, not across the sweeps
-  float fx[4], fy[4], ft[4];
+  const bool later = a.phi_in != nullptr;  // a later pass of an outer iteration: phi, ksi come from its first pass
   // Programmatic dependent launch: this grid may have been started while the previous pass was still
-  // draining.  Everything the previous pass does not write (u, v, the derivative planes) is loaded
+  // draining.  Everything the previous pass does not write (u, v, the derivative planes) is requested
   // first; du, dv, phi, ksi only after griddepcontrol.wait (= previous grid complete and flushed).
   if (a.pdl) asm volatile("griddepcontrol.launch_dependents;");
-  load_strip(a.u, sa, gx, w, t.uc);
-  load_strip(a.v, sa, gx, w, t.vc);
-  load_strip(a.fx, sa, gx, w, fx);
-  load_strip(a.fy, sa, gx, w, fy);
-  load_strip(a.ft, sa, gx, w, ft);
-  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (a.du_in) {
-    load_strip(a.du_in, sa, gx, w, du);
-    load_strip(a.dv_in, sa, gx, w, t.dv);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) du[i] = t.dv[i] = 0.f;
-  }
-
 
   for (int outer = 0; outer < a.outer; ++outer) {
     // (the sweep loop of the previous outer iteration ended with a barrier: every plane is free)
-    // resident mode: du of the previous outer iteration comes back from this thread's own store
-    if (outer > 0) load_strip(a.du_out, sa, gx, w, du);
-
-    // ------ phase A: remaining loads; motion tensor (solve_2d.cu:324-329 / 879-884); ksi (176-196) ------
+    // ------ phase A: loads; ksi (solve_2d.cu:176-196); hand-over of fx, fy, ft or the gradient tensor ------
     float phi[4];
-    {
-      float ksi[4];
-      if (outer > 0) {
-        load_strip(a.fx, sa, gx, w, fx);
-        load_strip(a.fy, sa, gx, w, fy);
-        load_strip(a.ft, sa, gx, w, ft);
+    stage_strip<P_U>(a.u, sa, gx, w, sb);
+    stage_strip<P_V>(a.v, sa, gx, w, sb);
+    if (later) {
+      // nothing is computed from these planes before phase C: all of them go straight to shared memory
+      if (!GRAD) {
+        stage_strip<P_FX>(a.fx, sa, gx, w, sb);
+        stage_strip<P_FY>(a.fy, sa, gx, w, sb);
+        stage_strip<P_FT>(a.ft, sa, gx, w, sb);
       }
-      if (a.phi_in) {
-        load_strip(a.phi_in, sa, gx, w, phi);
-        load_strip(a.ksi_in, sa, gx, w, ksi);
+      if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+      stage_strip<P_DU>(a.du_in, sa, gx, w, sb);
+      stage_strip<P_DV>(a.dv_in, sa, gx, w, sb);
+      stage_strip<P_PHI>(a.phi_in, sa, gx, w, sb);
+      stage_strip<P_KSI>(a.ksi_in, sa, gx, w, sb);
+    } else {
+      float fx[4], fy[4], ft[4], ksi[4];
+      load_strip(a.fx, sa, gx, w, fx);
+      load_strip(a.fy, sa, gx, w, fy);
+      load_strip(a.ft, sa, gx, w, ft);
+      if (outer == 0) {
+        if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (a.du_in) {
+          load_strip(a.du_in, sa, gx, w, du);
+          load_strip(a.dv_in, sa, gx, w, t.dv);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) du[i] = t.dv[i] = 0.f;
+        }
+      } else {
+        // resident mode: du of the previous outer iteration comes back from this thread's own store
+        // (dv is still in its registers)
+        load_strip(a.du_out, sa, gx, w, du);
       }
-      float J11[4], J22[4], J12[4], J13[4], J23[4];
+      // own pixel only; always the brightness tensor, also in gradient mode
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        J11[i] = fx[i] * fx[i];
-        J22[i] = fy[i] * fy[i];
-        J12[i] = fx[i] * fy[i];
-        J13[i] = fx[i] * ft[i];
-        J23[i] = fy[i] * ft[i];
-      }
-      if (!a.phi_in) {
-        // own pixel only; always the brightness tensor, also in gradient mode
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float d_u = du[i], d_v = t.dv[i];
-          const float ta = J13[i] + fmaf(J11[i], d_u, J12[i] * d_v);
-          const float tb = J23[i] + fmaf(J12[i], d_u, J22[i] * d_v);
-          const float tc = fmaf(ft[i], ft[i], fmaf(J13[i], d_u, J23[i] * d_v));
-          float sq = fmaf(d_u, ta, d_v * tb) + tc;
-          sq = sq * ((sq > 0.f) ? 1.f : 0.f);
-          const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
-          ksi[i] = 1.f / (q + q);
-        }
-      }
-      if (BORDER) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) ksi[i] = inside[i] ? ksi[i] : 0.f;
+        const float J11 = fx[i] * fx[i], J22 = fy[i] * fy[i], J12 = fx[i] * fy[i], J13 = fx[i] * ft[i], J23 = fy[i] * ft[i];
+        const float d_u = du[i], d_v = t.dv[i];
+        const float ta = J13 + fmaf(J11, d_u, J12 * d_v);
+        const float tb = J23 + fmaf(J12, d_u, J22 * d_v);
+        const float tc = fmaf(ft[i], ft[i], fmaf(J13, d_u, J23 * d_v));
+        float sq = fmaf(d_u, ta, d_v * tb) + tc;
+        sq = sq * ((sq > 0.f) ? 1.f : 0.f);
+        const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
+        ksi[i] = 1.f / (q + q);
       }
       sts4<P_KSI>(sb, ksi);
-      if (GRAD) {
-        load_strip(a.J[0], sa, gx, w, J11);
-        load_strip(a.J[1], sa, gx, w, J22);
-        load_strip(a.J[2], sa, gx, w, J12);
-        load_strip(a.J[3], sa, gx, w, J13);
-        load_strip(a.J[4], sa, gx, w, J23);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { J12[i] = -J12[i]; J13[i] = -J13[i]; J23[i] = -J23[i]; }
-        sts4<P_J11>(sb, J11);
-        sts4<P_J22>(sb, J22);
-        sts4<P_NJ12>(sb, J12);
-        sts4<P_NJ13>(sb, J13);
-        sts4<P_NJ23>(sb, J23);
-      } else {
+      if (!GRAD) {
         // brightness constancy: the tensor is five products of fx, fy, ft; three planes are handed to
-        // phase C instead of five, and the products need not stay live next to the ksi arithmetic
+        // phase C instead of five
         sts4<P_FX>(sb, fx);
         sts4<P_FY>(sb, fy);
         sts4<P_FT>(sb, ft);
       }
     }
+    if (GRAD) {
+      float J11[4], J22[4], J12[4], J13[4], J23[4];
+      load_strip(a.J[0], sa, gx, w, J11);
+      load_strip(a.J[1], sa, gx, w, J22);
+      load_strip(a.J[2], sa, gx, w, J12);
+      load_strip(a.J[3], sa, gx, w, J13);
+      load_strip(a.J[4], sa, gx, w, J23);
+#pragma unroll
+      for (int i = 0; i < 4; i++) { J12[i] = -J12[i]; J13[i] = -J13[i]; J23[i] = -J23[i]; }
+      sts4<P_J11>(sb, J11);
+      sts4<P_J22>(sb, J22);
+      sts4<P_NJ12>(sb, J12);
+      sts4<P_NJ13>(sb, J13);
+      sts4<P_NJ23>(sb, J23);
+    }
 
     if (TIMING) stamp(a, 1);
-    if (!a.phi_in) {
+    if (!later) {
       // ---------------- phase B: phi (solve_2d.cu:141-162) ----------------
-      sts4<P_U>(sb, t.uc);
-      sts4<P_V>(sb, t.vc);
       sts4<P_DU>(sb, du);
       sts4<P_DV>(sb, t.dv);
-      __syncthreads();
+      cp_async_wait_all();  // u, v of this strip have landed ...
+      __syncthreads();      // ... and everybody's are visible
+      lds4<P_U>(sb, t.uc);
+      lds4<P_V>(sb, t.vc);
       float dux[4], duy[4], dvx[4], dvy[4], num[4];
       const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
       const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
@@ -379,18 +392,31 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         const float r = sqrtf(s);
         phi[i] = 1.f / (r + r);
       }
+      sts4<P_PHI>(sb, phi);
+    } else {
+      cp_async_wait_all();
     }
-    sts4<P_PHI>(sb, phi);
-    __syncthreads();  // phi published; every reader of P_U..P_DV is done, so their aliases are free
+    __syncthreads();  // phi published; every reader of the neighbours' P_U..P_DV is done
     if (TIMING) stamp(a, 2);
 
     // ---------------- phase C: weights and denominators (solve_2d.cu:333-349, 363, 367) ----------------
     {
+      if (later) {  // this strip's own values, staged by phase A (their planes are recycled below)
+        lds4<P_U>(sb, t.uc);
+        lds4<P_V>(sb, t.vc);
+        lds4<P_DU>(sb, du);
+        lds4<P_DV>(sb, t.dv);
+        lds4<P_PHI>(sb, phi);
+      }
       const float pL = __shfl_up_sync(0xffffffffu, phi[3], 1), pR = __shfl_down_sync(0xffffffffu, phi[0], 1);
       float pU[4], pD[4], J11[4], J22[4], ksi[4];
       lds4<P_PHI>(sb_up, pU);
       lds4<P_PHI>(sb_dn, pD);
       lds4<P_KSI>(sb, ksi);
+      if (BORDER) {  // cells outside the image are inert
+#pragma unroll
+        for (int i = 0; i < 4; i++) ksi[i] = inside[i] ? ksi[i] : 0.f;
+      }
       if (GRAD) {
         lds4<P_J11>(sb, J11);
         lds4<P_J22>(sb, J22);
@@ -411,7 +437,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
         sts4<P_NJ13>(sb, nJ13);
         sts4<P_NJ23>(sb, nJ23);
       }
-      if (a.phi_out && !a.phi_in) {  // a later pass of this outer iteration reloads the robust weights
+      if (a.phi_out && !later) {  // a later pass of this outer iteration reloads the robust weights
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const int x = gx + i;
