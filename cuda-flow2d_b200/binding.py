@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 GREY, GRADIENT = 0, 1
-KERNEL_KINDS = 11  # FLOW2D_KERNEL_KINDS
+KERNEL_KINDS = 12  # FLOW2D_KERNEL_KINDS
+MAX_LEVELS = 256   # FLOW2D_MAX_LEVELS
 
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -35,6 +36,7 @@ class Params(C.Structure):
         ("sweeps_per_pass", C.c_int),
         ("resident_levels", C.c_int),
         ("throughput_mode", C.c_int),
+        ("report_residuals", C.c_int),
     ]
 
 
@@ -76,6 +78,9 @@ def lib():
         L.flow2d_synchronize.argtypes = [vp]
         L.flow2d_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_int), fp]
         L.flow2d_last_launch_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
+        dp = C.POINTER(C.c_double)
+        L.flow2d_level_residuals.argtypes = [vp, dp, dp, C.c_int, C.POINTER(C.c_int)]
+        L.flow2d_stage_residual.argtypes = [vp] + [vp] * 8 + [C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.POINTER(Params), dp, dp]
         L.flow2d_kernel_kind_name.argtypes = [C.c_int]
         L.flow2d_kernel_kind_name.restype = C.c_char_p
         L.flow2d_max_warp_level.restype = sz
@@ -167,6 +172,18 @@ class Flow2D:
         n, lv, ms = C.c_longlong(), C.c_int(), C.c_float()
         self._check(lib().flow2d_last_stats(self._h, C.byref(n), C.byref(lv), C.byref(ms)))
         return {"kernel_launches": n.value, "levels_run": lv.value, "device_ms": ms.value}
+
+    def level_residuals(self):
+        """(rms_u, rms_v) per level of the last compute with params.report_residuals = 1, coarsest level first."""
+        ru, rv, n = (C.c_double * MAX_LEVELS)(), (C.c_double * MAX_LEVELS)(), C.c_int()
+        self._check(lib().flow2d_level_residuals(self._h, ru, rv, MAX_LEVELS, C.byref(n)))
+        return [(ru[i], rv[i]) for i in range(n.value)]
+
+    def stage_residual(self, d_f0, d_f1w, d_u, d_v, d_du, d_dv, d_phi, d_ksi, w, h, hx, hy, params):
+        ru, rv = C.c_double(), C.c_double()
+        self._check(lib().flow2d_stage_residual(self._h, _ptr(d_f0), _ptr(d_f1w), _ptr(d_u), _ptr(d_v), _ptr(d_du), _ptr(d_dv),
+                                                _ptr(d_phi), _ptr(d_ksi), w, h, hx, hy, C.byref(params), C.byref(ru), C.byref(rv)))
+        return ru.value, rv.value
 
     def launch_counts(self):
         """Kernel launches of the last call, by kernel (flow2d_last_launch_counts)."""

@@ -48,12 +48,16 @@ struct flow2d_handle {
   float* c[C_COUNT] = {};
   long long launches = 0;
   long long kind_launches[FLOW2D_KERNEL_KINDS] = {};
+  double* d_residuals = nullptr;  // 2 doubles per pyramid level (sums of r_u^2, r_v^2), flow2d_params.report_residuals
+  int residual_levels = 0;        // levels of the last compute that recorded a residual
+  int residual_px[FLOW2D_MAX_LEVELS] = {};
   int levels_run = 0;
   float device_ms = 0.f;
   unsigned long long* timing = nullptr;  // debug: phase stamps of solve_pass (flow2d_debug_timing)
   cudaGraphExec_t graph_exec = nullptr;  // captured level schedule of the last (buffers, parameters) combination
   unsigned char graph_key[128] = {};
   long long graph_launches = 0;
+  int graph_residual_levels = 0;
   long long graph_kind_launches[FLOW2D_KERNEL_KINDS] = {};
   int graph_levels = 0;
   std::string err;
@@ -83,7 +87,7 @@ int fail(flow2d_handle* h, int code, const char* fmt, ...) {
 
 const char* const kKindNames[FLOW2D_KERNEL_KINDS] = {"blur", "resample", "warp", "derivatives", "grad_tensor", "solve_pass",
                                                       "solve_pass(resident)", "solve_small_pass", "solve_tiny", "add_median",
-                                                      "add"};
+                                                      "add", "residual"};
 
 int check_launch(flow2d_handle* h, int kind, int kernels) {
   cudaError_t e = cudaGetLastError();
@@ -362,6 +366,9 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
   const size_t W = h->W, H = h->H;
   cudaStream_t st = h->stream;
   h->levels_run = 0;
+  const bool residuals = p->report_residuals != 0 && !(slab && slab->world > 1);
+  h->residual_levels = 0;
+  if (residuals) CU_TRY(h, cudaMemsetAsync(h->d_residuals, 0, sizeof(double) * 2 * FLOW2D_MAX_LEVELS, st));
 
   // presmoothing (optical_flow_2d.cpp:218-246)
   const float* frame[2] = {frame_0, frame_1};
@@ -412,7 +419,14 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     TRY(check_launch(h, FLOW2D_K_WARP, 1));
     TRY(run_derivatives(h, g, fr[0], h->c[C_WARPED]));
     // solve (366-406)
-    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], false, p, slab));
+    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], residuals, p, slab));
+    if (residuals && h->residual_levels < FLOW2D_MAX_LEVELS && p->outer_iterations_count > 0 && p->inner_iterations_count > 0) {
+      const float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
+      launch_residual(st, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, h->constancy == FLOW2D_GRADIENT, u, v, h->c[C_DU0],
+                      h->c[C_DV0], h->c[C_PHI], h->c[C_KSI], g, p->equation_alpha, h->d_residuals + 2 * h->residual_levels);
+      TRY(check_launch(h, FLOW2D_K_RESIDUAL, 1));
+      h->residual_px[h->residual_levels++] = g.w * g.h;
+    }
     // u += du, v += dv, median (409-449); the finest level writes the caller's flow containers
     {
       const float* a[2] = {u, v};
@@ -460,12 +474,14 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   key.p.gaussian_sigma = p->gaussian_sigma; key.p.sweeps_per_pass = p->sweeps_per_pass;
   key.p.resident_levels = p->resident_levels;
   key.p.throughput_mode = p->throughput_mode;
+  key.p.report_residuals = p->report_residuals;
   key.timing = h->timing;
   if (h->graph_exec && std::memcmp(&key, h->graph_key, sizeof key) == 0) {
     CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
     h->launches = h->graph_launches;
     for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) h->kind_launches[k] = h->graph_kind_launches[k];
     h->levels_run = h->graph_levels;
+    h->residual_levels = h->graph_residual_levels;
     return FLOW2D_OK;
   }
   if (h->graph_exec) {
@@ -499,6 +515,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   h->graph_launches = h->launches;
   for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) h->graph_kind_launches[k] = h->kind_launches[k];
   h->graph_levels = h->levels_run;
+  h->graph_residual_levels = h->residual_levels;
   CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
   return FLOW2D_OK;
 }
@@ -544,6 +561,7 @@ void flow2d_default_params(flow2d_params* p) {
   p->sweeps_per_pass = 0;
   p->resident_levels = 0;
   p->throughput_mode = 0;
+  p->report_residuals = 0;
 }
 
 size_t flow2d_max_warp_level(size_t width, size_t height, float scale_factor) {
@@ -605,6 +623,11 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
     return FLOW2D_ERR_OUT_OF_MEMORY;
   }
   for (int i = 0; i < ncont; i++) h->c[i] = h->pool + csize * i;
+  if (cudaMalloc(&h->d_residuals, sizeof(double) * 2 * FLOW2D_MAX_LEVELS) != cudaSuccess) {
+    (void)cudaGetLastError();
+    flow2d_destroy(h);
+    return FLOW2D_ERR_OUT_OF_MEMORY;
+  }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
       solve_pass_configure() != cudaSuccess || cudaMemsetAsync(h->pool, 0, csize * ncont * sizeof(float), h->own_stream) != cudaSuccess ||
@@ -627,6 +650,7 @@ int flow2d_destroy(flow2d_handle* h) {
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->pool) cudaFree(h->pool);
+  if (h->d_residuals) cudaFree(h->d_residuals);
   delete h;
   return FLOW2D_OK;
 }
@@ -648,6 +672,43 @@ int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launches, int* l
   if (kernel_launches) *kernel_launches = h->launches;
   if (levels_run) *levels_run = h->levels_run;
   if (device_ms) *device_ms = h->device_ms;
+  return FLOW2D_OK;
+}
+
+int flow2d_level_residuals(flow2d_handle* h, double* rms_u, double* rms_v, int capacity, int* levels) {
+  STAGE_PROLOGUE(h);
+  if (levels) *levels = h->residual_levels;
+  if (h->residual_levels == 0 || capacity <= 0) return FLOW2D_OK;
+  double sums[2 * FLOW2D_MAX_LEVELS];
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(sums, h->d_residuals, sizeof(double) * 2 * h->residual_levels, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < h->residual_levels && i < capacity; i++) {
+    if (rms_u) rms_u[i] = std::sqrt(sums[2 * i] / h->residual_px[i]);
+    if (rms_v) rms_v[i] = std::sqrt(sums[2 * i + 1] / h->residual_px[i]);
+  }
+  return FLOW2D_OK;
+}
+
+int flow2d_stage_residual(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1_warped, const float* d_u,
+                          const float* d_v, const float* d_du, const float* d_dv, const float* d_phi, const float* d_ksi,
+                          size_t w, size_t hh, float hx, float hy, const flow2d_params* p, double* rms_u, double* rms_v) {
+  STAGE_PROLOGUE(h);
+  if (!d_frame_0 || !d_frame_1_warped || !d_u || !d_v || !d_du || !d_dv || !d_phi || !d_ksi || !p)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null pointer");
+  if (w < 2 || hh < 2 || w > h->W || hh > h->H) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "level %zux%zu does not fit the handle", w, hh);
+  const LevelGeom g = geom(h, w, hh, hx, hy);
+  TRY(run_derivatives(h, g, d_frame_0, d_frame_1_warped));
+  CU_TRY(h, cudaMemsetAsync(h->d_residuals, 0, sizeof(double) * 2, h->stream));
+  const float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
+  launch_residual(h->stream, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, h->constancy == FLOW2D_GRADIENT, d_u, d_v, d_du, d_dv,
+                  d_phi, d_ksi, g, p->equation_alpha, h->d_residuals);
+  TRY(check_launch(h, FLOW2D_K_RESIDUAL, 1));
+  double sums[2];
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpy(sums, h->d_residuals, sizeof sums, cudaMemcpyDeviceToHost));
+  h->residual_levels = 0;
+  if (rms_u) *rms_u = std::sqrt(sums[0] / ((double)w * (double)hh));
+  if (rms_v) *rms_v = std::sqrt(sums[1] / ((double)w * (double)hh));
   return FLOW2D_OK;
 }
 

@@ -57,4 +57,11 @@ void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int
 bool solve_tiny_fits(int w, int h);
 void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad);
 
+// ---- residual.cu (opt-in diagnostics, not on the default path) ----
+struct ResidualJ { const float* p[5]; };
+// adds the sums of r_u^2 and r_v^2 over the level to sums[0], sums[1]
+void launch_residual(cudaStream_t st, const float* fx, const float* fy, const float* ft, const float* const* J, bool grad,
+                     const float* u, const float* v, const float* du, const float* dv, const float* phi, const float* ksi,
+                     const LevelGeom& g, float alpha, double* sums);
+
 }  // namespace flow2d

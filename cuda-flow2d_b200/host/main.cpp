@@ -10,6 +10,8 @@
 //       flow between every pair of consecutive frames of a sequence, several pairs in flight at once
 //       (host/sequence.h); 8-bit / float32 frames told apart by file size; writes
 //       <out>NNNN_flow-u-W-H.raw / NNNN_flow-v-W-H.raw (and NNNN_res.pgm / NNNN_amp-W-H.raw on request)
+//   any pair form + trailing --residuals                                                                   (new)
+//       prints the RMS residual of every level's last linear system (flow2d_level_residuals)
 // Differences: no getchar() at exit; the 8-bit reader is wired to Mode@imageType="8-bit";
 // files are also looked up under Input/Path@inputPath when they are not found in the CWD.
 #include <cmath>
@@ -111,6 +113,12 @@ int main(int argc, char** argv) {
   std::printf("//----------------------------------------------------------------------//\n");
 
   if (argc >= 2 && string(argv[1]) == "--sequence") return run_sequence(argc, argv);
+  // optional trailing flag of the pair forms (not in the reference): per-level residual norms on stdout
+  bool report_residuals = false;
+  if (argc >= 2 && string(argv[argc - 1]) == "--residuals") {
+    report_residuals = true;
+    --argc;
+  }
 
   size_t width = 584, height = 388;
   size_t warp_levels_count = 50;  // src/main.cpp:70-80
@@ -200,6 +208,7 @@ int main(int argc, char** argv) {
   params.PushValuePtr("equation_data", &equation_data);
   params.PushValuePtr("median_radius", &median_radius);
   params.PushValuePtr("gaussian_sigma", &gaussian_sigma);
+  if (report_residuals) params.PushValuePtr("report_residuals", &report_residuals);
 
   optical_flow.ComputeFlow(frame_0, frame_1, flow_u, flow_v, params);
 

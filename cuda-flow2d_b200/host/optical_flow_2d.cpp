@@ -64,6 +64,8 @@ void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u
       !get(params, GetName(), "median_radius", &p.median_radius) ||
       !get(params, GetName(), "gaussian_sigma", &p.gaussian_sigma))
     return;
+  // optional, beyond the reference's nine keys: "report_residuals" (bool*) prints the per-level residual norms
+  if (void* opt = params.GetValuePtr("report_residuals")) p.report_residuals = *static_cast<bool*>(opt) ? 1 : 0;
   for (Data2D* d : {&frame_0, &frame_1, &flow_u, &flow_v})
     if (d->Width() != size_.width || d->Height() != size_.height || !d->DataPtr()) {
       std::printf("Error: '%s': frames and flow fields must be %zux%zu.\n", GetName(), size_.width, size_.height);
@@ -79,5 +81,11 @@ void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u
   int levels = 0;
   flow2d_last_stats(handle_, &launches, &levels, &last_gpu_time_ms);
   if (!silent) std::printf("Levels: %d, kernel launches: %lld\n", levels, launches);
+  if (p.report_residuals) {
+    double ru[FLOW2D_MAX_LEVELS], rv[FLOW2D_MAX_LEVELS];
+    int n = 0;
+    if (flow2d_level_residuals(handle_, ru, rv, FLOW2D_MAX_LEVELS, &n) == FLOW2D_OK)
+      for (int i = 0; i < n; i++) std::printf("Level %3d (coarsest first): residual rms u %.6e  v %.6e\n", i, ru[i], rv[i]);
+  }
   std::printf("Total GPU computation time: % 4.4fs\n", last_gpu_time_ms / 1000.);
 }

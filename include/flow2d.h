@@ -69,9 +69,12 @@ typedef struct flow2d_params {
   int    throughput_mode;        /* 0 = schedule for the latency of ONE frame pair (mid-size levels use the one-thread-per-
                                     pixel pass, which trades redundant halo work for a 3x shorter dependent chain);
                                     1 = schedule for throughput: several handles share the GPU, redundant work is not free */
+  int    report_residuals;       /* opt-in diagnostics (no reference counterpart, see flow2d_level_residuals): 1 = record
+                                    the residual norm of every level's last linear system; results are unchanged */
 } flow2d_params;
 
 #define FLOW2D_MAX_SWEEPS_PER_PASS 7
+#define FLOW2D_MAX_LEVELS 256    /* residuals are recorded for at most this many levels (the coarsest ones) */
 
 /* Fills *p with the reference's argv-form defaults (src/main.cpp:70-80). */
 FLOW2D_API void flow2d_default_params(flow2d_params* p);
@@ -119,10 +122,27 @@ FLOW2D_API int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launc
 enum {
   FLOW2D_K_BLUR = 0, FLOW2D_K_RESAMPLE, FLOW2D_K_WARP, FLOW2D_K_DERIVATIVES, FLOW2D_K_GRAD_TENSOR, FLOW2D_K_SOLVE_PASS,
   FLOW2D_K_SOLVE_RESIDENT, FLOW2D_K_SOLVE_SMALL_PASS, FLOW2D_K_SOLVE_TINY, FLOW2D_K_ADD_MEDIAN, FLOW2D_K_ADD,
+  FLOW2D_K_RESIDUAL,
   FLOW2D_KERNEL_KINDS
 };
 FLOW2D_API int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts /* [FLOW2D_KERNEL_KINDS] */);
 FLOW2D_API const char* flow2d_kernel_kind_name(int kind);
+
+/* ---- opt-in convergence diagnostics -----------------------------------------
+ * The reference runs fixed iteration counts and computes no norm (cuda_operation_solve_2d.cpp:229-299).
+ * With flow2d_params.report_residuals = 1 every level additionally records the RMS residual of the
+ * lagged linear system of its LAST outer iteration, after that iteration's inner sweeps:
+ *   r_u = ksi*(-J13 - J12*dv - J11*du) + sum_n a_n*((u_n+du_n) - (u+du)),   r_v likewise
+ * (the quantities of solve_2d.cu:333-374; zero at the fixed point of the Jacobi update).  One extra
+ * kernel per level (warp-shuffle + atomic reduction in double precision); flow results are unchanged.
+ * flow2d_level_residuals waits for the handle's stream and returns the values of the last
+ * flow2d_compute*() call, coarsest level first.  Not recorded in the row-slab mode. */
+FLOW2D_API int flow2d_level_residuals(flow2d_handle* h, double* rms_u, double* rms_v, int capacity, int* levels);
+/* The same number for one level on caller containers (phi, ksi as returned by flow2d_stage_solve). Synchronous. */
+FLOW2D_API int flow2d_stage_residual(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1_warped,
+                          const float* d_u, const float* d_v, const float* d_du, const float* d_dv,
+                          const float* d_phi, const float* d_ksi, size_t w, size_t hh, float hx, float hy,
+                          const flow2d_params* p, double* rms_u, double* rms_v);
 
 /* ---- level table: replaces OpticalFlowBase2D::GetMaxWarpLevel and the per-level size formulas ---
  * (src/optical_flow/optical_flow_base_2d.cpp:36-59, src/optical_flow/optical_flow_2d.cpp:268-272).

@@ -360,6 +360,69 @@ void oracle_sweep_grad(const float* f0, const float* f1, const float* u, const f
   free(FT);
 }
 
+/* EXTENSION (see the header): residual of the system jacobi_update relaxes. */
+void oracle_residual(const float* f0, const float* f1, const float* u, const float* v, const float* du,
+                     const float* dv, const float* phi, const float* ksi, size_t w, size_t h, size_t pitch,
+                     float hx, float hy, float alpha, int constancy, double* rms_u, double* rms_v) {
+  const float hx4 = hx * 4.f, hy4 = hy * 4.f;
+  const float hx_2 = alpha / (hx * hx), hy_2 = alpha / (hy * hy);
+  const float hx_1 = (float)(1.0 / (2.0 * (double)hx)), hy_1 = (float)(1.0 / (2.0 * (double)hy));
+  long W = (long)w, Hh = (long)h;
+  float* FX = (float*)malloc(sizeof(float) * pitch * h);
+  float* FY = (float*)malloc(sizeof(float) * pitch * h);
+  float* FT = (float*)malloc(sizeof(float) * pitch * h);
+  for (long y = 0; y < Hh; y++) {
+    long ym = mirror(y - 1, Hh), yp = mirror(y + 1, Hh);
+    for (long x = 0; x < W; x++) {
+      long xm = mirror(x - 1, W), xp = mirror(x + 1, W);
+      FX[IDX(x, y)] = (((f0[IDX(xp, y)] - f0[IDX(xm, y)]) + f1[IDX(xp, y)]) - f1[IDX(xm, y)]) / hx4;
+      FY[IDX(x, y)] = (((f0[IDX(x, yp)] - f0[IDX(x, ym)]) + f1[IDX(x, yp)]) - f1[IDX(x, ym)]) / hy4;
+      FT[IDX(x, y)] = f1[IDX(x, y)] - f0[IDX(x, y)];
+    }
+  }
+  double su2 = 0.0, sv2 = 0.0;
+  for (long y = 0; y < Hh; y++)
+    for (long x = 0; x < W; x++) {
+      float J11, J22, J12, J13, J23;
+      if (constancy == ORACLE_GRADIENT) {
+        long tx = x % 16, ty = y % 8;
+        long xl = (tx == 0) ? x : x - 1, xr = (tx == 15 || x + 1 >= W) ? x : x + 1;
+        long yu = (ty == 0) ? y : y - 1, yb = (ty == 7 || y + 1 >= Hh) ? y : y + 1;
+        float fxx = (FX[IDX(xr, y)] - FX[IDX(xl, y)]) * hx_1, fxy = (FX[IDX(x, yb)] - FX[IDX(x, yu)]) * hy_1;
+        float fyy = (FY[IDX(x, yb)] - FY[IDX(x, yu)]) * hy_1;
+        float fxt = (FT[IDX(xr, y)] - FT[IDX(xl, y)]) * hx_1, fyt = (FT[IDX(x, yb)] - FT[IDX(x, yu)]) * hy_1;
+        J11 = fmaf(fxx, fxx, fxy * fxy); J22 = fmaf(fxy, fxy, fyy * fyy); J12 = fmaf(fxx, fxy, fxy * fyy);
+        J13 = fmaf(fxx, fxt, fxy * fyt); J23 = fmaf(fxy, fxt, fyy * fyt);
+      } else {
+        float fx = FX[IDX(x, y)], fy = FY[IDX(x, y)], ft = FT[IDX(x, y)];
+        J11 = fx * fx; J22 = fy * fy; J12 = fx * fy; J13 = fx * ft; J23 = fy * ft;
+      }
+      long xm = mirror(x - 1, W), xp = mirror(x + 1, W), ym = mirror(y - 1, Hh), yp = mirror(y + 1, Hh);
+      float wxp = hx_2 * ((x < W - 1) ? 1.f : 0.f), wxm = hx_2 * ((x > 0) ? 1.f : 0.f);
+      float wyp = hy_2 * ((y < Hh - 1) ? 1.f : 0.f), wym = hy_2 * ((y > 0) ? 1.f : 0.f);
+      float pc = phi[IDX(x, y)];
+      double axp = wxp * ((phi[IDX(xp, y)] + pc) * 0.5f), axm = wxm * ((phi[IDX(xm, y)] + pc) * 0.5f);
+      double ayp = wyp * ((phi[IDX(x, yp)] + pc) * 0.5f), aym = wym * ((phi[IDX(x, ym)] + pc) * 0.5f);
+      double k = ksi[IDX(x, y)], d_u = du[IDX(x, y)], d_v = dv[IDX(x, y)];
+      double sU = (double)u[IDX(x, y)] + d_u, sV = (double)v[IDX(x, y)] + d_v;
+#define SU(X, Y) ((double)u[IDX(X, Y)] + (double)du[IDX(X, Y)])
+#define SV(X, Y) ((double)v[IDX(X, Y)] + (double)dv[IDX(X, Y)])
+      double lap_u = axm * (SU(xm, y) - sU) + axp * (SU(xp, y) - sU) + ayp * (SU(x, yp) - sU) + aym * (SU(x, ym) - sU);
+      double lap_v = axm * (SV(xm, y) - sV) + axp * (SV(xp, y) - sV) + ayp * (SV(x, yp) - sV) + aym * (SV(x, ym) - sV);
+#undef SU
+#undef SV
+      double ru = k * (-(double)J13 - (double)J12 * d_v - (double)J11 * d_u) + lap_u;
+      double rv = k * (-(double)J23 - (double)J12 * d_u - (double)J22 * d_v) + lap_v;
+      su2 += ru * ru;
+      sv2 += rv * rv;
+    }
+  free(FX);
+  free(FY);
+  free(FT);
+  *rms_u = sqrt(su2 / ((double)w * (double)h));
+  *rms_v = sqrt(sv2 / ((double)w * (double)h));
+}
+
 /* cuda_operation_solve_2d.cpp:229-299 */
 void oracle_solve_level(const float* f0, const float* f1, const float* u, const float* v,
                         float* du, float* dv, float* phi, float* ksi, float* tmp_du, float* tmp_dv,

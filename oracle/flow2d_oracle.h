@@ -84,6 +84,13 @@ void oracle_solve_level(const float* f0, const float* f1, const float* u, const 
                         size_t w, size_t h, size_t pitch, float hx, float hy,
                         const oracle_params* p);
 
+/* EXTENSION beyond the reference (which computes no norm): RMS residual of the lagged linear system of
+ * jacobi_update (solve_2d.cu:333-374) for given phi, ksi and increment; weights in fp32 as the sweep forms
+ * them, everything else in double.  Checks flow2d_stage_residual / flow2d_level_residuals. */
+void oracle_residual(const float* f0, const float* f1, const float* u, const float* v, const float* du,
+                     const float* dv, const float* phi, const float* ksi, size_t w, size_t h, size_t pitch,
+                     float hx, float hy, float alpha, int constancy, double* rms_u, double* rms_v);
+
 /* add_2d.cu:33-46 */
 void oracle_add(float* a, const float* b, size_t w, size_t h, size_t pitch);
 /* median_2d.cu:87-299 + cuda_operation_median_2d.cpp:100-111. Returns 0 if a filter/copy ran,

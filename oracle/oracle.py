@@ -168,6 +168,19 @@ def solve_level(f0, f1, u, v, hx, hy, params):
     return du, dv, phi, ksi
 
 
+def residual(f0, f1, u, v, du, dv, phi, ksi, hx, hy, alpha, constancy=GREY):
+    """EXTENSION (no reference counterpart): RMS residual of the lagged linear system; returns (rms_u, rms_v)."""
+    f0, f1, u, v, du, dv, phi, ksi = map(_f32, (f0, f1, u, v, du, dv, phi, ksi))
+    h, w = f0.shape
+    ru, rv = C.c_double(), C.c_double()
+    fn = lib().oracle_residual
+    fn.restype = None
+    fn.argtypes = [C.c_void_p] * 8 + [C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_int,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    fn(_p(f0), _p(f1), _p(u), _p(v), _p(du), _p(dv), _p(phi), _p(ksi), w, h, w, hx, hy, alpha, constancy, C.byref(ru), C.byref(rv))
+    return ru.value, rv.value
+
+
 def median(img, radius):
     img = _f32(img)
     h, w = img.shape

@@ -159,3 +159,21 @@ def test_sequence_gradient_settings_and_read_failure(synth, oracle, tmp_path):
     # ... an output directory that does not exist by the writer thread (exit code 4)
     frames[2].tofile(tmp_path / "s02.raw")
     assert _run(CLI, ["--sequence", w, h, "missing_dir/"] + names, tmp_path).returncode == 4
+
+
+def test_pair_form_with_residuals_flag(rub, tmp_path):
+    """Trailing --residuals (not in the reference): same output files, plus one residual line per pyramid level."""
+    f0, f1 = rub
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    f0.tofile(tmp_path / "r1.raw")
+    f1.tofile(tmp_path / "r2.raw")
+    r = _run(CLI, ["r1.raw", "r2.raw", 584, 388, "x_", "a/"], tmp_path)
+    q = _run(CLI, ["r1.raw", "r2.raw", 584, 388, "x_", "b/", "--residuals"], tmp_path)
+    assert r.returncode == 0 and q.returncode == 0, q.stdout.decode()[-2000:]
+    lines = [l for l in q.stdout.decode().splitlines() if l.startswith("Level ") and "residual rms" in l]
+    assert len(lines) == 47 and b"residual rms" not in r.stdout
+    vals = [float(l.split()[-3]) for l in lines] + [float(l.split()[-1]) for l in lines]
+    assert all(np.isfinite(v) and v >= 0 for v in vals)
+    for name in ("x_flow-u-584-388.raw", "x_flow-v-584-388.raw", "x_amp-584-388.raw", "x_res.pgm"):
+        assert (tmp_path / "a" / name).read_bytes() == (tmp_path / "b" / name).read_bytes(), name

@@ -269,3 +269,22 @@ def test_threads_do_not_change_results(oracle, synth):
     b = oracle.compute_flow(f0, f1, p)
     oracle.set_num_threads(n)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_residual_extension(oracle):
+    """oracle_residual (an extension: the reference computes no norm) -- zero for identical frames at zero flow,
+    falling with the number of Jacobi sweeps, and a fixed point of the sweep has (near) zero residual."""
+    from cuda_flow2d_b200 import synth  # pure numpy generator
+    f0, f1, _, _ = synth.make_pair(40, 32, 4, U1=1.0)
+    z = np.zeros_like(f0)
+    one = np.ones_like(f0)
+    assert oracle.residual(f0, f0, z, z, z, z, one, one, 1.0, 1.0, 5.0) == (0.0, 0.0)
+    seen = []
+    for inner in (1, 10, 100, 3000):
+        p = oracle.make_params(outer=1, inner=inner, alpha=2.0)
+        du, dv, phi, ksi = oracle.solve_level(f0, f1, z, z, 1.0, 1.0, p)
+        seen.append(sum(oracle.residual(f0, f1, z, z, du, dv, phi, ksi, 1.0, 1.0, 2.0)))
+    assert seen[0] > seen[1] > seen[2] > seen[3] and seen[3] < 0.05 * seen[0], seen
+    # sweeping once more from a (numerically) converged state changes the increment by about residual / diagonal
+    du2 = oracle.sweep(f0, f1, z, z, du, dv, phi, ksi, 1.0, 1.0, 2.0)[0]
+    assert np.abs(du2 - du).max() < 1e-3
