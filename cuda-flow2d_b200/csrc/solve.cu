@@ -888,4 +888,170 @@ void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int
   else cudaLaunchKernelEx(&cfg, solve_small_pass_kernel<false>, a);
 }
 
+// ---------------------------------------------------------------------------------------------
+// solve_small_level: ALL outer iterations of a mid-size level in one cooperative launch.  Same
+// regions, same arithmetic as solve_small_pass; the CTAs stay resident, keep u, v, fx, fy, ft (or the
+// gradient tensor) of their region in registers for the whole level, and meet at a grid barrier
+// after every outer iteration, when the new increment of the neighbouring tiles is re-read from
+// global memory (L2; ld.global.cg, the L1 is not coherent).  Replaces outer launches + their
+// dependent-launch gaps (~6 us each) by outer grid barriers (~1 us each).  Needs every CTA of the
+// grid to be resident at once, hence at most one CTA per SM and a cooperative launch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* gen = bar + 1;
+    const unsigned g = *gen;
+    __threadfence();  // this CTA's stores of the iteration before its arrival
+    if (atomicAdd(bar, 1u) == nblocks - 1) {
+      *bar = 0;  // count first, then the generation that releases the others
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g) { }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(TS * TS, 1) solve_small_level_kernel(const SolveArgs a, float* du_b, float* dv_b, unsigned* bar) {
+  __shared__ float sU[TS * TS], sV[TS * TS], sDU[TS * TS], sDV[TS * TS], sPHI[TS * TS];
+  __shared__ float sSU[2][TS * TS], sSV[2][TS * TS];
+  const int w = a.w, h = a.h;
+  const int t = threadIdx.x, lx = t & (TS - 1), ly = t / TS;
+  const int ox0 = blockIdx.x * a.ow, oy0 = blockIdx.y * a.oh;
+  const int ox1 = min(w, ox0 + a.ow), oy1 = min(h, oy0 + a.oh);
+  const int gx = ox0 - a.halo_x + lx, gy = oy0 - a.halo_y + ly;
+  const bool inside = gx >= 0 && gx < w && gy >= 0 && gy < h;
+  const bool mine = gx >= ox0 && gx < ox1 && gy >= oy0 && gy < oy1;
+  const int il = (gx == 0 || lx == 0) ? t + 1 : t - 1, ir = (gx == w - 1 || lx == TS - 1) ? t - 1 : t + 1;
+  const int iu = (gy == 0 || ly == 0) ? t + TS : t - TS, id = (gy == h - 1 || ly == TS - 1) ? t - TS : t + TS;
+  const size_t g = (size_t)min(max(gy, 0), h - 1) * a.pitch + min(max(gx, 0), w - 1);
+  const unsigned nblocks = gridDim.x * gridDim.y;
+
+  const float uc = a.u[g], vc = a.v[g], fx = a.fx[g], fy = a.fy[g], ft = a.ft[g];
+  float J11, J22, nJ12, nJ13, nJ23;
+  if (GRAD) {
+    J11 = a.J[0][g]; J22 = a.J[1][g]; nJ12 = -a.J[2][g]; nJ13 = -a.J[3][g]; nJ23 = -a.J[4][g];
+  } else {
+    J11 = fx * fx; J22 = fy * fy; nJ12 = -(fx * fy); nJ13 = -(fx * ft); nJ23 = -(fy * ft);
+  }
+  sU[t] = uc; sV[t] = vc;
+  const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
+  const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
+  const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
+  const float wxp = hx_2 * ((gx < w - 1) ? 1.f : 0.f), wxm = hx_2 * ((gx > 0) ? 1.f : 0.f);
+  const float wyp = hy_2 * ((gy < h - 1) ? 1.f : 0.f), wym = hy_2 * ((gy > 0) ? 1.f : 0.f);
+  // the increment ping-pongs between (a.du_out, a.dv_out) and (du_b, dv_b); the last outer iteration writes a.du_out
+  float du = 0.f, dv = 0.f;
+  for (int outer = 0; outer < a.outer; ++outer) {
+    const bool to_a = ((a.outer - 1 - outer) & 1) == 0;
+    float* wdu = to_a ? a.du_out : du_b;
+    float* wdv = to_a ? a.dv_out : dv_b;
+    if (outer > 0) {  // what the previous outer iteration left, own tile and neighbours' tiles alike
+      const float* rdu = to_a ? du_b : a.du_out;
+      const float* rdv = to_a ? dv_b : a.dv_out;
+      du = __ldcg(rdu + g);
+      dv = __ldcg(rdv + g);
+    }
+    sDU[t] = du; sDV[t] = dv;
+    __syncthreads();
+    // solve_2d.cu:141-162
+    const float dux = div_rn1(((sU[ir] - sU[il]) + sDU[ir]) - sDU[il], hx2, rhx2);
+    const float duy = div_rn1(((sU[id] - sU[iu]) + sDU[id]) - sDU[iu], hy2, rhy2);
+    const float dvx = div_rn1(((sV[ir] - sV[il]) + sDV[ir]) - sDV[il], hx2, rhx2);
+    const float dvy = div_rn1(((sV[id] - sV[iu]) + sDV[id]) - sDV[iu], hy2, rhy2);
+    float s = duy * duy;
+    s = fmaf(dux, dux, s);
+    s = fmaf(dvx, dvx, s);
+    s = fmaf(dvy, dvy, s);
+    s = fmaf(a.e_smooth, a.e_smooth, s);
+    const float rr = sqrtf(s);
+    const float phi = 1.f / (rr + rr);
+    // solve_2d.cu:176-196: always the brightness tensor
+    float ksi;
+    {
+      const float j11 = fx * fx, j22 = fy * fy, j12 = fx * fy, j13 = fx * ft, j23 = fy * ft;
+      const float ta = j13 + fmaf(j11, du, j12 * dv);
+      const float tb = j23 + fmaf(j12, du, j22 * dv);
+      const float tc = fmaf(ft, ft, fmaf(j13, du, j23 * dv));
+      float sq = fmaf(du, ta, dv * tb) + tc;
+      sq = sq * ((sq > 0.f) ? 1.f : 0.f);
+      const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
+      ksi = inside ? 1.f / (q + q) : 0.f;
+    }
+    sPHI[t] = phi;
+    __syncthreads();
+    // solve_2d.cu:333-349, 363, 367; cells outside the image are inert
+    float axp = wxp * ((sPHI[ir] + phi) * 0.5f);
+    float axm = wxm * ((sPHI[il] + phi) * 0.5f);
+    float ayp = wyp * ((sPHI[id] + phi) * 0.5f);
+    float aym = wym * ((sPHI[iu] + phi) * 0.5f);
+    const float sumH = ((axp + axm) + ayp) + aym;
+    float denU = fmaf(J11, ksi, sumH), denV = fmaf(J22, ksi, sumH);
+    if (!inside) { axp = axm = ayp = aym = 0.f; denU = denV = 1.f; }
+    const float rU = fast_path_rcp(denU), rV = fast_path_rcp(denV);
+    sSU[0][t] = uc + du;
+    sSV[0][t] = vc + dv;
+    __syncthreads();
+    for (int k = 0; k < a.sweeps; ++k) {
+      const float* cu = sSU[k & 1];
+      const float* cv = sSV[k & 1];
+      // solve_2d.cu:350-367 as compiled: mul, then fma chain xm, xp, yp, ym
+      float sumU = axm * (cu[il] - uc);
+      sumU = fmaf(axp, cu[ir] - uc, sumU);
+      sumU = fmaf(ayp, cu[id] - uc, sumU);
+      sumU = fmaf(aym, cu[iu] - uc, sumU);
+      float sumV = axm * (cv[il] - vc);
+      sumV = fmaf(axp, cv[ir] - vc, sumV);
+      sumV = fmaf(ayp, cv[id] - vc, sumV);
+      sumV = fmaf(aym, cv[iu] - vc, sumV);
+      du = div_rn1(fmaf(ksi, fmaf(nJ12, dv, nJ13), sumU), denU, rU);
+      dv = div_rn1(fmaf(ksi, fmaf(nJ12, du, nJ23), sumV), denV, rV);
+      sSU[(k + 1) & 1][t] = uc + du;
+      sSV[(k + 1) & 1][t] = vc + dv;
+      __syncthreads();
+    }
+    if (mine) {
+      const size_t o = (size_t)gy * a.pitch + gx;
+      wdu[o] = du;
+      wdv[o] = dv;
+      if (a.phi_out && outer == a.outer - 1) { a.phi_out[o] = phi; a.ksi_out[o] = ksi; }
+    }
+    if (outer + 1 < a.outer) grid_barrier(bar, nblocks);
+  }
+}
+
+static int g_small_level_max_ctas = 0;
+
+int solve_small_level_max_ctas() {
+  if (g_small_level_max_ctas == 0) {
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_small_level_kernel<false>, TS * TS, 0) == cudaSuccess)
+      g_small_level_max_ctas = sms * (per_sm > 1 ? 1 : per_sm);  // one CTA per SM: the point is latency
+    if (g_small_level_max_ctas <= 0) g_small_level_max_ctas = -1;
+  }
+  return g_small_level_max_ctas > 0 ? g_small_level_max_ctas : 0;
+}
+
+void launch_solve_small_level(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, float* du_b, float* dv_b,
+                              unsigned* bar) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid_x, grid_y);
+  cfg.blockDim = dim3(TS * TS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (grad) cudaLaunchKernelEx(&cfg, solve_small_level_kernel<true>, a, du_b, dv_b, bar);
+  else cudaLaunchKernelEx(&cfg, solve_small_level_kernel<false>, a, du_b, dv_b, bar);
+}
+
 }  // namespace flow2d
