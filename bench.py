@@ -132,6 +132,24 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one solve_pass launch of this workload from the committed
+    `ncu --set full` capture (profiles/r01/solve_<workload>_ncu_summary.txt, written by tools/gpu_round.sh), in bytes;
+    None if there is no capture of this workload."""
+    path = os.path.join(ROOT, "profiles", "r01", "solve_%s_ncu_summary.txt" % workload)
+    if workload != "c2" or not os.path.exists(path):
+        return None
+    total, unit = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        for line in open(path):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[2].strip("[]'\"")) * unit[f[1]]
+    except Exception:
+        return None
+    return total or None
+
+
 def make_frames(wl, rank):
     if wl.get("rub"):  # the reference's own frame pair, committed as a fixture (tests/golden/README.md)
         z = np.load(os.path.join(ROOT, "tests", "golden", "rub_u8.npz"))
@@ -399,7 +417,7 @@ def run_ours(args, wl, rank, world, local_rank):
         roof = {"kernel": "%s_kernel<%s> (%d launches per solve, %.3g Jacobi sweeps per launch on average)" %
                           (kname.replace("(resident)", ""), "true" if wl.get("gradient") else "false", n_pass, sweeps),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "launch_us": launch_ms * 1e3,
+                "traffic": ncu_traffic(args.workload), "peak_source": peak_src, "launch_us": launch_ms * 1e3,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "unfused_equivalent_gbs": achieved * sweeps,
                 "note": "temporally blocked: one launch does the work of %g reference sweeps (40 B/px each), so the kernel is "

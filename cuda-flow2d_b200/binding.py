@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 GREY, GRADIENT = 0, 1
-KERNEL_KINDS = 13  # FLOW2D_KERNEL_KINDS
+KERNEL_KINDS = 12  # FLOW2D_KERNEL_KINDS
 MAX_LEVELS = 256   # FLOW2D_MAX_LEVELS
 
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5

@@ -48,7 +48,6 @@ struct flow2d_handle {
   float* c[C_COUNT] = {};
   long long launches = 0;
   long long kind_launches[FLOW2D_KERNEL_KINDS] = {};
-  unsigned* d_gridbar = nullptr;  // count + generation of the grid barrier of solve_small_level
   double* d_residuals = nullptr;  // 2 doubles per pyramid level (sums of r_u^2, r_v^2), flow2d_params.report_residuals
   int residual_levels = 0;        // levels of the last compute that recorded a residual
   int residual_px[FLOW2D_MAX_LEVELS] = {};
@@ -88,7 +87,7 @@ int fail(flow2d_handle* h, int code, const char* fmt, ...) {
 
 const char* const kKindNames[FLOW2D_KERNEL_KINDS] = {"blur", "resample", "warp", "derivatives", "grad_tensor", "solve_pass",
                                                       "solve_pass(resident)", "solve_small_pass", "solve_tiny", "add_median",
-                                                      "add", "residual", "solve_small_level"};
+                                                      "add", "residual"};
 
 int check_launch(flow2d_handle* h, int kind, int kernels) {
   cudaError_t e = cudaGetLastError();
@@ -226,24 +225,6 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   }
   if (S > FLOW2D_MAX_SWEEPS_PER_PASS) S = FLOW2D_MAX_SWEEPS_PER_PASS;
   const int npass = (inner + S - 1) / S;
-  // Mid-size level, one pass per outer iteration, one frame pair at a time: all outer iterations in ONE
-  // cooperative launch (grid barrier between them) if its 32x32 regions fit the SMs one to one.
-  static const bool no_fused = std::getenv("FLOW2D_NO_FUSED_LEVELS") != nullptr;  // A/B switch for measurements
-  if (npass == 1 && outer > 1 && p->resident_levels == 0 && !p->throughput_mode && !(slab && slab->world > 1) && !no_fused) {
-    const int so = kSmallTS - 2 * (S + 1);
-    const int gx = so >= 8 ? (g.w + so - 1) / so : 0, gy = so >= 8 ? (g.h + so - 1) / so : 0;
-    if (gx > 0 && (long long)gx * gy <= solve_small_level_max_ctas()) {
-      a.du_in = a.dv_in = nullptr;
-      a.phi_in = a.ksi_in = nullptr;
-      a.du_out = du_a; a.dv_out = dv_a;
-      a.phi_out = want_phi ? phi : nullptr; a.ksi_out = want_phi ? ksi : nullptr;
-      a.sweeps = S; a.outer = outer;
-      a.halo_x = a.halo_y = S + 1;
-      a.ow = a.oh = so;
-      launch_solve_small_level(h->stream, a, grad, gx, gy, du_b, dv_b, h->d_gridbar);
-      return check_launch(h, FLOW2D_K_SOLVE_SMALL_LEVEL, 1);
-    }
-  }
   const long long total = (long long)outer * npass;
   float* bufs[2][2] = {{du_a, dv_a}, {du_b, dv_b}};
   long long pass = 0;
@@ -642,8 +623,7 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
     return FLOW2D_ERR_OUT_OF_MEMORY;
   }
   for (int i = 0; i < ncont; i++) h->c[i] = h->pool + csize * i;
-  if (cudaMalloc(&h->d_gridbar, 2 * sizeof(unsigned)) != cudaSuccess || cudaMemset(h->d_gridbar, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
-      cudaMalloc(&h->d_residuals, sizeof(double) * 2 * FLOW2D_MAX_LEVELS) != cudaSuccess) {
+  if (cudaMalloc(&h->d_residuals, sizeof(double) * 2 * FLOW2D_MAX_LEVELS) != cudaSuccess) {
     (void)cudaGetLastError();
     flow2d_destroy(h);
     return FLOW2D_ERR_OUT_OF_MEMORY;
@@ -671,7 +651,6 @@ int flow2d_destroy(flow2d_handle* h) {
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->pool) cudaFree(h->pool);
   if (h->d_residuals) cudaFree(h->d_residuals);
-  if (h->d_gridbar) cudaFree(h->d_gridbar);
   delete h;
   return FLOW2D_OK;
 }

@@ -53,12 +53,6 @@ void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_
 // a.ow = a.oh = kSmallTS - 2 * halo; phi/ksi are always computed in the pass (a.phi_in must be null)
 constexpr int kSmallTS = 32;
 void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y);
-// all outer iterations of a mid-size level in ONE cooperative launch (same regions as launch_solve_small_pass, a.outer =
-// outer iterations, result in a.du_out/a.dv_out, du_b/dv_b scratch, bar = two zero-initialised words of the handle);
-// the grid must not exceed solve_small_level_max_ctas() (0 = cooperative launch not available)
-int solve_small_level_max_ctas();
-void launch_solve_small_level(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, float* du_b, float* dv_b,
-                              unsigned* bar);
 // whole solve of a level of <= 1024 pixels in one CTA, one thread per pixel (a.outer, a.sweeps = inner)
 bool solve_tiny_fits(int w, int h);
 void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad);

@@ -122,7 +122,7 @@ FLOW2D_API int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launc
 enum {
   FLOW2D_K_BLUR = 0, FLOW2D_K_RESAMPLE, FLOW2D_K_WARP, FLOW2D_K_DERIVATIVES, FLOW2D_K_GRAD_TENSOR, FLOW2D_K_SOLVE_PASS,
   FLOW2D_K_SOLVE_RESIDENT, FLOW2D_K_SOLVE_SMALL_PASS, FLOW2D_K_SOLVE_TINY, FLOW2D_K_ADD_MEDIAN, FLOW2D_K_ADD,
-  FLOW2D_K_RESIDUAL, FLOW2D_K_SOLVE_SMALL_LEVEL,
+  FLOW2D_K_RESIDUAL,
   FLOW2D_KERNEL_KINDS
 };
 FLOW2D_API int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts /* [FLOW2D_KERNEL_KINDS] */);
