@@ -196,7 +196,14 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   }
   // resident mode: the whole level (plus a one-cell apron) fits one CTA's region
   const bool fits = g.w + 4 + 1 <= kSolveLW && g.h + 1 + 1 <= kSolveLH;
-  if (fits && p->resident_levels >= 0) {
+  // ... unless one frame pair at a time is being solved and an outer iteration is a single one-thread-per-
+  // pixel pass: a handful of 32x32 CTAs, one launch per outer iteration, then beat one CTA that carries four
+  // pixels per thread through all of them (measured on the rub pair: ~240 us against 420-520 us per level).
+  // With several handles sharing the GPU the resident CTA wins again: it occupies one SM instead of nine.
+  const bool small_pass_instead = p->resident_levels == 0 && !p->throughput_mode && outer > 1 &&
+                                  (p->sweeps_per_pass == 0 || p->sweeps_per_pass >= inner) &&
+                                  inner <= FLOW2D_MAX_SWEEPS_PER_PASS && kSmallTS - 2 * (inner + 1) >= 8;
+  if (fits && p->resident_levels >= 0 && !small_pass_instead) {
     a.du_in = a.dv_in = nullptr;
     a.phi_in = a.ksi_in = nullptr;
     a.du_out = du_a; a.dv_out = dv_a;
