@@ -181,6 +181,8 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   a.w = g.w; a.h = g.h; a.pitch = g.pitch;
   a.hx = g.hx; a.hy = g.hy;
   a.alpha = p->equation_alpha; a.e_smooth = p->equation_smoothness; a.e_data = p->equation_data;
+  a.hx_2 = a.alpha / (a.hx * a.hx);
+  a.hy_2 = a.alpha / (a.hy * a.hy);
   a.timing = h->timing;
   a.y0 = 0; a.y1 = g.h;
 
@@ -202,7 +204,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   // With several handles sharing the GPU the resident CTA wins again: it occupies one SM instead of nine.
   const bool small_pass_instead = p->resident_levels == 0 && !p->throughput_mode && outer > 1 &&
                                   (p->sweeps_per_pass == 0 || p->sweeps_per_pass >= inner) &&
-                                  inner <= FLOW2D_MAX_SWEEPS_PER_PASS && kSmallTS - 2 * (inner + 1) >= 8;
+                                  inner <= FLOW2D_MAX_SWEEPS_PER_PASS && kSmallTS - 2 * (inner + 1) >= 4;
   if (fits && p->resident_levels >= 0 && !small_pass_instead) {
     a.du_in = a.dv_in = nullptr;
     a.phi_in = a.ksi_in = nullptr;
@@ -307,22 +309,30 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       a.pdl = (pass > 0 && !no_pdl && !after_exchange) ? 1 : 0;  // the first pass follows the derivatives kernel
       after_exchange = false;
       // Mid-size levels cannot fill the GPU with 64x48 regions; there the latency of one CTA is what
-      // counts and the one-thread-per-pixel pass (32x32 regions) is faster as long as its many more
-      // CTAs still fit a few waves.  Measured per wave on B200: ~3.5 us against ~11 us.
+      // counts and the one-thread-per-pixel pass is faster as long as its many more CTAs still fit a few
+      // waves.  Time model fitted to tools/level_timing.py on B200 (us per outer iteration, launch gap included):
+      //   tiled 64x48 tiles   0.7 + 11.1 * max(1, tiles / 148)
+      //   ts x ts regions     1.0 + ceil(regions / 148) * (2.5 + 1.6 * ts^2 / 1024)
       bool small = false;
       if (npass == 1 && p->resident_levels != 2 && p->resident_levels != -1 && !p->throughput_mode) {
-        const int so = kSmallTS - 2 * (s + 1);
-        if (so >= 8) {
-          const long long n_small = (long long)((g.w + so - 1) / so) * ((vb - va + so - 1) / so);
-          const long long n_big = (long long)((g.w + a.ow - 1) / a.ow) * ((vb - va + a.oh - 1) / a.oh);
-          const double t_small = (double)((n_small + 147) / 148) * 3.5, t_big = (double)((n_big + 147) / 148) * 11.0;
-          small = t_small < t_big;
-          if (small) {
-            a.halo_x = a.halo_y = s + 1;
-            a.ow = a.oh = so;
-            launch_solve_small_pass(h->stream, a, grad, (g.w + so - 1) / so, (vb - va + so - 1) / so);
-            TRY(check_launch(h, FLOW2D_K_SOLVE_SMALL_PASS, 1));
-          }
+        const long long n_big = (long long)((g.w + a.ow - 1) / a.ow) * ((vb - va + a.oh - 1) / a.oh);
+        double t_best = 0.7 + 11.1 * (n_big > 148 ? (double)n_big / 148.0 : 1.0);
+        int ts_best = 0;
+        static const int kRegion[3] = {32, 24, 16};
+        for (int ts : kRegion) {
+          const int so = ts - 2 * (s + 1);
+          if (so < 4) continue;
+          const long long n = (long long)((g.w + so - 1) / so) * ((vb - va + so - 1) / so);
+          const double t = 1.0 + (double)((n + 147) / 148) * (2.5 + 1.6 * (ts * ts) / 1024.0);
+          if (t < t_best) { t_best = t; ts_best = ts; }
+        }
+        if (ts_best) {
+          small = true;
+          const int so = ts_best - 2 * (s + 1);
+          a.halo_x = a.halo_y = s + 1;
+          a.ow = a.oh = so;
+          launch_solve_small_pass(h->stream, a, grad, (g.w + so - 1) / so, (vb - va + so - 1) / so, ts_best);
+          TRY(check_launch(h, FLOW2D_K_SOLVE_SMALL_PASS, 1));
         }
       }
       if (!small) {

@@ -34,6 +34,7 @@ struct SolveArgs {
   float *phi_out, *ksi_out;       // null = do not store the robust weights
   int w, h, pitch;
   float hx, hy, alpha, e_smooth, e_data;
+  float hx_2, hy_2;               // alpha / hx^2, alpha / hy^2 (solve_2d.cu:333-334), computed by the caller in fp32
   int sweeps;                     // Jacobi sweeps in this pass
   int outer;                      // 1, or (resident mode, grid 1x1) the number of outer iterations
   int ow, oh;                     // output tile of one CTA (ow % 4 == 0)
@@ -49,10 +50,10 @@ cudaError_t solve_pass_configure();
 // rows > 0: launch only that many region rows (resident mode of a level with few rows)
 void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows = 0);
 
-// one pass of a mid-size level with one thread per pixel: 32x32 regions, a.halo_x = a.halo_y = a.sweeps + 1,
-// a.ow = a.oh = kSmallTS - 2 * halo; phi/ksi are always computed in the pass (a.phi_in must be null)
+// one pass of a mid-size level with one thread per pixel: ts x ts regions (ts = 32, 24 or 16), a.halo_x = a.halo_y =
+// a.sweeps + 1, a.ow = a.oh = ts - 2 * halo; phi/ksi are always computed in the pass (a.phi_in must be null)
 constexpr int kSmallTS = 32;
-void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y);
+void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int ts = kSmallTS);
 // whole solve of a level of <= 1024 pixels in one CTA, one thread per pixel (a.outer, a.sweeps = inner)
 bool solve_tiny_fits(int w, int h);
 void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad);

@@ -139,8 +139,8 @@ __device__ __forceinline__ void stage_strip(const float* __restrict__ p, const S
 // 2^-60 .. 2^60 (far inside FCHK's safe range), or a zero dividend (quotient = a*r = +-0 with the
 // right sign).  Everything else takes the plain `a / d`.
 __device__ __forceinline__ bool in_fast_range(float x) {
-  const unsigned e = (__float_as_uint(x) >> 23) & 0xffu;
-  return (e - 67u) < 120u;
+  const float m = fabsf(x);  // two FSETP with |x| operands; false for NaN, infinities, zeros and denormals
+  return m >= 0x1p-60f && m < 0x1p60f;
 }
 __device__ __forceinline__ float fast_path_rcp(float d) {  // 0 = "divisor not safe, use a / d"
   float r0;
@@ -447,7 +447,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
           }
         }
       }
-      const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
+      const float hx_2 = a.hx_2, hy_2 = a.hy_2;  // alpha / h^2, divided once on the host (IEEE, same bits)
       // Neumann boundary through zero weights (solve_2d.cu:337-340)
       float wyp = hy_2, wym = hy_2;
       if (BORDER) {
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(kTinyMax, 1) solve_tiny_kernel(const SolveArgs
   }
   const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
   const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
-  const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
+  const float hx_2 = a.hx_2, hy_2 = a.hy_2;  // alpha / h^2, divided once on the host (IEEE, same bits)
   const float wxp = hx_2 * ((x < w - 1) ? 1.f : 0.f), wxm = hx_2 * ((x > 0) ? 1.f : 0.f);
   const float wyp = hy_2 * ((y < h - 1) ? 1.f : 0.f), wym = hy_2 * ((y > 0) ? 1.f : 0.f);
 
@@ -773,14 +773,15 @@ void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad) {
 // of one CTA, and one pixel per thread cuts the dependent chain of a pass by four.  Mask-free like
 // solve_pass: every cell is updated in every sweep, exactness shrinks by one ring per sweep.
 // ---------------------------------------------------------------------------------------------
-constexpr int TS = kSmallTS;  // 32
-
-template <bool GRAD>
+// The region edge TS is 32, 24 or 16: the kernel is bound by instruction issue inside the CTA (~760
+// instructions per pixel and pass, one warp per 32 pixels), so a smaller region is a proportionally shorter
+// pass as long as the level's regions still fit the SMs one to one; the scheduler picks the size per level.
+template <bool GRAD, int TS>
 __global__ void __launch_bounds__(TS * TS, 1) solve_small_pass_kernel(const SolveArgs a) {
   __shared__ float sU[TS * TS], sV[TS * TS], sDU[TS * TS], sDV[TS * TS], sPHI[TS * TS];
   __shared__ float sSU[2][TS * TS], sSV[2][TS * TS];
   const int w = a.w, h = a.h;
-  const int t = threadIdx.x, lx = t & (TS - 1), ly = t / TS;
+  const int t = threadIdx.x, ly = t / TS, lx = t - ly * TS;
   const int ox0 = blockIdx.x * a.ow, oy0 = a.y0 + blockIdx.y * a.oh;
   const int ox1 = min(w, ox0 + a.ow), oy1 = min(a.y1, oy0 + a.oh);
   const int gx = ox0 - a.halo_x + lx, gy = oy0 - a.halo_y + ly;
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(TS * TS, 1) solve_small_pass_kernel(const Solv
   sU[t] = uc; sV[t] = vc; sDU[t] = du; sDV[t] = dv;
   const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
   const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
-  const float hx_2 = a.alpha / (a.hx * a.hx), hy_2 = a.alpha / (a.hy * a.hy);
+  const float hx_2 = a.hx_2, hy_2 = a.hy_2;  // alpha / h^2, divided once on the host (IEEE, same bits)
   __syncthreads();
   // solve_2d.cu:141-162
   const float dux = div_rn1(((sU[ir] - sU[il]) + sDU[ir]) - sDU[il], hx2, rhx2);
@@ -873,10 +874,16 @@ __global__ void __launch_bounds__(TS * TS, 1) solve_small_pass_kernel(const Solv
   }
 }
 
-void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y) {
+template <int TS>
+static void launch_small_ts(const cudaLaunchConfig_t& cfg, const SolveArgs& a, bool grad) {
+  if (grad) cudaLaunchKernelEx(&cfg, solve_small_pass_kernel<true, TS>, a);
+  else cudaLaunchKernelEx(&cfg, solve_small_pass_kernel<false, TS>, a);
+}
+
+void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int ts) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid_x, grid_y);
-  cfg.blockDim = dim3(TS * TS);
+  cfg.blockDim = dim3(ts * ts);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -884,8 +891,9 @@ void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = a.pdl ? 1 : 0;
-  if (grad) cudaLaunchKernelEx(&cfg, solve_small_pass_kernel<true>, a);
-  else cudaLaunchKernelEx(&cfg, solve_small_pass_kernel<false>, a);
+  if (ts == 16) launch_small_ts<16>(cfg, a, grad);
+  else if (ts == 24) launch_small_ts<24>(cfg, a, grad);
+  else launch_small_ts<32>(cfg, a, grad);
 }
 
 }  // namespace flow2d
