@@ -410,26 +410,29 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     flow2d_level_geometry(W, H, p->warp_scale_factor, level, &cw, &ch, &hx, &hy);
     const LevelGeom g = geom(h, cw, ch, hx, hy);
 
-    // frames of this level: always restricted from the full-resolution frames (279-305)
+    // frames of this level: always restricted from the full-resolution frames (279-305);
+    // flow of this level: zero, or prolongated from the previous level (308-341).
+    // Both resamplings share one x launch and one y launch (the increment containers are free at this point
+    // and serve as the x-pass scratch of the flow).
     const float* fr[2] = {frame[0], frame[1]};
+    ResampleJob jobs[4];
+    int njobs = 0;
     if (level != 0) {
-      float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP1]};
-      float* res[2] = {h->c[C_RES0], h->c[C_RES1]};
-      launch_resample(st, frame, tmp, res, 2, (int)W, (int)H, g.w, g.h, g.pitch);
-      TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
-      fr[0] = res[0]; fr[1] = res[1];
+      jobs[njobs++] = ResampleJob{frame[0], h->c[C_TMP0], h->c[C_RES0], (int)W, (int)H, g.w, g.h};
+      jobs[njobs++] = ResampleJob{frame[1], h->c[C_TMP1], h->c[C_RES1], (int)W, (int)H, g.w, g.h};
+      fr[0] = h->c[C_RES0]; fr[1] = h->c[C_RES1];
     }
-    // flow of this level: zero, or prolongated from the previous level (308-341)
     if (pw == 0) {
       CU_TRY(h, cudaMemset2DAsync(u, h->pitch * 4, 0, cw * 4, ch, st));
       CU_TRY(h, cudaMemset2DAsync(v, h->pitch * 4, 0, cw * 4, ch, st));
     } else {
-      const float* in[2] = {u, v};
-      float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP1]};
-      float* out[2] = {u2, v2};
-      launch_resample(st, in, tmp, out, 2, (int)pw, (int)ph, g.w, g.h, g.pitch);
-      TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
+      jobs[njobs++] = ResampleJob{u, h->c[C_DU1], u2, (int)pw, (int)ph, g.w, g.h};
+      jobs[njobs++] = ResampleJob{v, h->c[C_DV1], v2, (int)pw, (int)ph, g.w, g.h};
       std::swap(u, u2); std::swap(v, v2);
+    }
+    if (njobs) {
+      launch_resample_batch(st, jobs, njobs, g.pitch);
+      TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
     }
     // backward registration (344-363) and the level's derivative planes
     launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g);

@@ -9,6 +9,14 @@ namespace flow2d {
 void launch_blur(cudaStream_t st, const float* in, float* out, int w, int h, int pitch, const GaussTaps& taps);
 void launch_resample(cudaStream_t st, const float* const* in, float* const* tmp, float* const* out, int count,
                      int iw, int ih, int ow, int oh, int pitch);
+// the same for up to four images of different sizes in one x launch + one y launch (tmp holds ow x ih)
+struct ResampleJob {
+  const float* in;
+  float* tmp;
+  float* out;
+  int iw, ih, ow, oh;
+};
+void launch_resample_batch(cudaStream_t st, const ResampleJob* jobs, int count, int pitch);
 void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float* u, const float* v, float* out,
                  const LevelGeom& g);
 void launch_derivatives(cudaStream_t st, const float* f0, const float* f1w, float* fx, float* fy, float* ft,

@@ -67,24 +67,28 @@ void launch_blur(cudaStream_t st, const float* in, float* out, int w, int h, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// Area resampling, one axis per kernel, two images per launch (blockIdx.z).
+// Area resampling, one axis per kernel, up to four images per launch (blockIdx.z): the two frames that a
+// level restricts and the two flow components it prolongates go through the same two launches.
 // The index path is the reference's fp32 arithmetic verbatim (resample_2d.cu:44-51):
 //   delta = in/(float)out (div.rn), left_f = x*delta, right_f = (x+1)*delta (plain mul),
 //   left_i = floor, right_i = min(in, ceil); accumulation value = fma(frac, in[..], value).
 // ---------------------------------------------------------------------------------------------
-struct ResamplePair {
-  const float* in[2];
-  float* out[2];
+struct ResampleBatch {  // up to four images per launch (blockIdx.z), each with its own geometry
+  ResampleJob job[4];
 };
 
 template <bool ALONG_X>
 __global__ void __launch_bounds__(256)
-resample_kernel(ResamplePair io, int out_w, int out_h, int in_n, int out_n, int pitch) {
+resample_kernel(ResampleBatch b, int pitch) {
+  const ResampleJob& jb = b.job[blockIdx.z];
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  // out_w x out_h = what this pass writes; in_n -> out_n along the pass direction
+  const int out_w = jb.ow, out_h = ALONG_X ? jb.ih : jb.oh;
+  const int in_n = ALONG_X ? jb.iw : jb.ih, out_n = ALONG_X ? jb.ow : jb.oh;
   if (x >= out_w || y >= out_h) return;
-  const float* __restrict__ in = blockIdx.z ? io.in[1] : io.in[0];
-  float* __restrict__ out = blockIdx.z ? io.out[1] : io.out[0];
+  const float* __restrict__ in = ALONG_X ? jb.in : jb.tmp;
+  float* __restrict__ out = ALONG_X ? jb.tmp : jb.out;
   const int o = ALONG_X ? x : y;
   const float delta = (float)in_n / (float)out_n;
   const float normalization = (float)out_n / (float)in_n;
@@ -106,20 +110,29 @@ resample_kernel(ResamplePair io, int out_w, int out_h, int in_n, int out_n, int 
   out[(size_t)y * pitch + x] = value * normalization;
 }
 
+// One x pass and one y pass for `count` (1..4) images of possibly different sizes.
+void launch_resample_batch(cudaStream_t st, const ResampleJob* jobs, int count, int pitch) {
+  ResampleBatch b;
+  int gw = 0, gh_x = 0, gh_y = 0;
+  for (int i = 0; i < 4; i++) {
+    b.job[i] = jobs[i < count ? i : 0];
+    if (i < count) {
+      gw = jobs[i].ow > gw ? jobs[i].ow : gw;
+      gh_x = jobs[i].ih > gh_x ? jobs[i].ih : gh_x;
+      gh_y = jobs[i].oh > gh_y ? jobs[i].oh : gh_y;
+    }
+  }
+  dim3 block(32, 8);
+  resample_kernel<true><<<dim3((gw + 31) / 32, (gh_x + 7) / 8, count), block, 0, st>>>(b, pitch);
+  resample_kernel<false><<<dim3((gw + 31) / 32, (gh_y + 7) / 8, count), block, 0, st>>>(b, pitch);
+}
+
 // (iw x ih) -> (ow x oh) for `count` (1 or 2) images; tmp[] are scratch containers.
 void launch_resample(cudaStream_t st, const float* const* in, float* const* tmp, float* const* out, int count,
                      int iw, int ih, int ow, int oh, int pitch) {
-  ResamplePair px, py;
-  for (int i = 0; i < 2; i++) {
-    int k = i < count ? i : 0;
-    px.in[i] = in[k]; px.out[i] = tmp[k];
-    py.in[i] = tmp[k]; py.out[i] = out[k];
-  }
-  dim3 block(32, 8);
-  dim3 gx((ow + 31) / 32, (ih + 7) / 8, count);
-  resample_kernel<true><<<gx, block, 0, st>>>(px, ow, ih, iw, ow, pitch);
-  dim3 gy((ow + 31) / 32, (oh + 7) / 8, count);
-  resample_kernel<false><<<gy, block, 0, st>>>(py, ow, oh, ih, oh, pitch);
+  ResampleJob jobs[2];
+  for (int i = 0; i < count && i < 2; i++) jobs[i] = ResampleJob{in[i], tmp[i], out[i], iw, ih, ow, oh};
+  launch_resample_batch(st, jobs, count < 2 ? count : 2, pitch);
 }
 
 // ---------------------------------------------------------------------------------------------

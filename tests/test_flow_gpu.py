@@ -106,3 +106,20 @@ def test_full_size_properties(pkg, synth, torch_):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     z = fl.compute(f0, f0, pkg.default_params(levels=5, outer=2))
     assert not z[0].any() and not z[1].any()
+
+
+def test_launch_counts_by_kernel(pkg, synth, torch_):
+    """flow2d_last_launch_counts splits flow2d_last_stats' launch count by kernel; a replayed graph reports the same."""
+    w, h = 200, 150
+    f0, f1, _, _ = synth.make_pair(w, h, 2, U1=1.0)
+    fl = pkg.Flow2D(w, h)
+    p = pkg.default_params(levels=50, scale=0.8, outer=3, inner=5)
+    fl.compute(f0, f1, p)
+    counts = fl.launch_counts()
+    assert sum(counts.values()) == fl.stats()["kernel_launches"]
+    levels = fl.stats()["levels_run"]
+    assert counts["warp"] == counts["derivatives"] == counts["add_median"] == levels
+    assert counts["blur"] == 2 and counts["resample"] == 2 * levels  # one x + one y launch per level for frames and flow together
+    assert any(k.startswith("solve") for k in counts)
+    fl.compute(f0, f1, p)
+    assert fl.launch_counts() == counts
