@@ -656,105 +656,147 @@ __device__ __forceinline__ float div_rn1(float a, float d, float r) {
   return q;
 }
 
+// ---- one pixel per thread: the part solve_tiny and solve_small_pass share -------------------------
+// Nine shared planes of N floats (N = pixels of the CTA); a thread keeps five 32-bit shared addresses
+// (its own cell and its four neighbours in plane 0) and reaches every plane with a compile-time byte
+// offset, so a neighbour read is one LDS without address arithmetic; the sweep loop is unrolled by the
+// parity of the exchange buffer.
+enum { Q_U = 0, Q_V, Q_DU, Q_DV, Q_PHI, Q_SU0, Q_SV0, Q_SU1, Q_SV1, kOnePxPlanes };
+
+template <int N, int PLANE>
+__device__ __forceinline__ float ldq(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1 + %2];" : "=f"(v) : "r"(addr), "n"(PLANE * N * 4) : "memory");
+  return v;
+}
+template <int N, int PLANE>
+__device__ __forceinline__ void stq(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0 + %1], %2;" ::"r"(addr), "n"(PLANE * N * 4), "f"(v) : "memory");
+}
+
+struct OnePx {
+  unsigned ac, al, ar, au, ad;           // shared addresses in plane 0: own cell, left, right, up, down
+  float uc, vc, fx, fy, ft;              // constants of the pixel
+  float J11, J22, nJ12, nJ13, nJ23;
+  float wxp, wxm, wyp, wym;              // alpha / h^2, zero across the image border
+  float hx2, hy2, rhx2, rhy2;
+  float e_smooth, e_data;
+  bool live;                             // false = the cell is inert (outside the image): zero weights, ksi = 0
+};
+
+// One outer iteration: publish du, dv; phi, ksi; weights; `sweeps` Jacobi sweeps.  The caller has put uc, vc
+// into planes Q_U, Q_V.  Ends with a barrier.  Same operations, in the same order, as solve_pass.
+template <int N>
+__device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, float& du, float& dv, float& phi, float& ksi) {
+  stq<N, Q_DU>(c.ac, du);
+  stq<N, Q_DV>(c.ac, dv);
+  __syncthreads();
+  {
+    // solve_2d.cu:141-162
+    const float dux = div_rn1(((ldq<N, Q_U>(c.ar) - ldq<N, Q_U>(c.al)) + ldq<N, Q_DU>(c.ar)) - ldq<N, Q_DU>(c.al), c.hx2, c.rhx2);
+    const float duy = div_rn1(((ldq<N, Q_U>(c.ad) - ldq<N, Q_U>(c.au)) + ldq<N, Q_DU>(c.ad)) - ldq<N, Q_DU>(c.au), c.hy2, c.rhy2);
+    const float dvx = div_rn1(((ldq<N, Q_V>(c.ar) - ldq<N, Q_V>(c.al)) + ldq<N, Q_DV>(c.ar)) - ldq<N, Q_DV>(c.al), c.hx2, c.rhx2);
+    const float dvy = div_rn1(((ldq<N, Q_V>(c.ad) - ldq<N, Q_V>(c.au)) + ldq<N, Q_DV>(c.ad)) - ldq<N, Q_DV>(c.au), c.hy2, c.rhy2);
+    float s = duy * duy;
+    s = fmaf(dux, dux, s);
+    s = fmaf(dvx, dvx, s);
+    s = fmaf(dvy, dvy, s);
+    s = fmaf(c.e_smooth, c.e_smooth, s);
+    const float rr = sqrtf(s);
+    phi = 1.f / (rr + rr);
+    // solve_2d.cu:176-196: always the brightness tensor
+    const float j11 = c.fx * c.fx, j22 = c.fy * c.fy, j12 = c.fx * c.fy, j13 = c.fx * c.ft, j23 = c.fy * c.ft;
+    const float ta = j13 + fmaf(j11, du, j12 * dv);
+    const float tb = j23 + fmaf(j12, du, j22 * dv);
+    const float tc = fmaf(c.ft, c.ft, fmaf(j13, du, j23 * dv));
+    float sq = fmaf(du, ta, dv * tb) + tc;
+    sq = sq * ((sq > 0.f) ? 1.f : 0.f);
+    const float q = sqrtf(fmaf(c.e_data, c.e_data, sq));
+    ksi = c.live ? 1.f / (q + q) : 0.f;
+  }
+  stq<N, Q_PHI>(c.ac, phi);
+  __syncthreads();
+  // solve_2d.cu:333-349, 363, 367; cells outside the image are inert
+  float axp = c.wxp * ((ldq<N, Q_PHI>(c.ar) + phi) * 0.5f);
+  float axm = c.wxm * ((ldq<N, Q_PHI>(c.al) + phi) * 0.5f);
+  float ayp = c.wyp * ((ldq<N, Q_PHI>(c.ad) + phi) * 0.5f);
+  float aym = c.wym * ((ldq<N, Q_PHI>(c.au) + phi) * 0.5f);
+  const float sumH = ((axp + axm) + ayp) + aym;
+  float denU = fmaf(c.J11, ksi, sumH), denV = fmaf(c.J22, ksi, sumH);
+  if (!c.live) { axp = axm = ayp = aym = 0.f; denU = denV = 1.f; }
+  const float rU = fast_path_rcp(denU), rV = fast_path_rcp(denV);
+  const float uc = c.uc, vc = c.vc;
+  stq<N, Q_SU0>(c.ac, uc + du);
+  stq<N, Q_SV0>(c.ac, vc + dv);
+  __syncthreads();
+  // solve_2d.cu:350-367 as compiled: mul, then fma chain xm, xp, yp, ym
+  auto sweep = [&](auto even) {
+    constexpr bool EVEN = decltype(even)::value;  // sweep 0, 2, ...: reads buffer 0, writes buffer 1
+    constexpr int CU = EVEN ? Q_SU0 : Q_SU1, CV = EVEN ? Q_SV0 : Q_SV1, NU = EVEN ? Q_SU1 : Q_SU0, NV = EVEN ? Q_SV1 : Q_SV0;
+    float sumU = axm * (ldq<N, CU>(c.al) - uc);
+    sumU = fmaf(axp, ldq<N, CU>(c.ar) - uc, sumU);
+    sumU = fmaf(ayp, ldq<N, CU>(c.ad) - uc, sumU);
+    sumU = fmaf(aym, ldq<N, CU>(c.au) - uc, sumU);
+    float sumV = axm * (ldq<N, CV>(c.al) - vc);
+    sumV = fmaf(axp, ldq<N, CV>(c.ar) - vc, sumV);
+    sumV = fmaf(ayp, ldq<N, CV>(c.ad) - vc, sumV);
+    sumV = fmaf(aym, ldq<N, CV>(c.au) - vc, sumV);
+    du = div_rn1(fmaf(ksi, fmaf(c.nJ12, dv, c.nJ13), sumU), denU, rU);
+    dv = div_rn1(fmaf(ksi, fmaf(c.nJ12, du, c.nJ23), sumV), denV, rV);
+    stq<N, NU>(c.ac, uc + du);
+    stq<N, NV>(c.ac, vc + dv);
+    __syncthreads();
+  };
+  for (int k = 0; k < sweeps; k += 2) {
+    sweep(std::true_type{});
+    if (k + 1 < sweeps) sweep(std::false_type{});
+  }
+}
+
 template <bool GRAD>
 __global__ void __launch_bounds__(kTinyMax, 1) solve_tiny_kernel(const SolveArgs a) {
-  __shared__ float sU[kTinyMax], sV[kTinyMax], sDU[kTinyMax], sDV[kTinyMax], sPHI[kTinyMax];
-  __shared__ float sSU[2][kTinyMax], sSV[2][kTinyMax];
+  __shared__ __align__(16) float sq[kOnePxPlanes * kTinyMax];
   const int w = a.w, h = a.h, n = w * h;
   const int t = threadIdx.x;
-  const bool on = t < n;
+  const bool on = t < n;  // (threads beyond the level only take part in the barriers; their cells are inert)
   const int x = on ? t % w : 0, y = on ? t / w : 0;
   // mirrored neighbours (index -1 -> 1, n -> n-2)
   const int il = y * w + (x == 0 ? 1 : x - 1), ir = y * w + (x == w - 1 ? w - 2 : x + 1);
   const int iu = (y == 0 ? 1 : y - 1) * w + x, id = (y == h - 1 ? h - 2 : y + 1) * w + x;
   const size_t g = (size_t)y * a.pitch + x;
+  asm volatile("griddepcontrol.launch_dependents;");
 
-  float uc = 0.f, vc = 0.f, fx = 0.f, fy = 0.f, ft = 0.f, du = 0.f, dv = 0.f;
-  float J11 = 0.f, J22 = 0.f, nJ12 = 0.f, nJ13 = 0.f, nJ23 = 0.f;
+  OnePx c;
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sq);
+  c.ac = base + 4u * t; c.al = base + 4u * (on ? il : t); c.ar = base + 4u * (on ? ir : t);
+  c.au = base + 4u * (on ? iu : t); c.ad = base + 4u * (on ? id : t);
+  c.uc = c.vc = c.fx = c.fy = c.ft = 0.f;
+  c.J11 = c.J22 = c.nJ12 = c.nJ13 = c.nJ23 = 0.f;
+  float du = 0.f, dv = 0.f;
   if (on) {
-    uc = a.u[g]; vc = a.v[g]; fx = a.fx[g]; fy = a.fy[g]; ft = a.ft[g];
+    c.uc = a.u[g]; c.vc = a.v[g]; c.fx = a.fx[g]; c.fy = a.fy[g]; c.ft = a.ft[g];
     if (a.du_in) { du = a.du_in[g]; dv = a.dv_in[g]; }
     if (GRAD) {
-      J11 = a.J[0][g]; J22 = a.J[1][g]; nJ12 = -a.J[2][g]; nJ13 = -a.J[3][g]; nJ23 = -a.J[4][g];
+      c.J11 = a.J[0][g]; c.J22 = a.J[1][g]; c.nJ12 = -a.J[2][g]; c.nJ13 = -a.J[3][g]; c.nJ23 = -a.J[4][g];
     } else {
-      J11 = fx * fx; J22 = fy * fy; nJ12 = -(fx * fy); nJ13 = -(fx * ft); nJ23 = -(fy * ft);
+      c.J11 = c.fx * c.fx; c.J22 = c.fy * c.fy; c.nJ12 = -(c.fx * c.fy); c.nJ13 = -(c.fx * c.ft); c.nJ23 = -(c.fy * c.ft);
     }
-    sU[t] = uc; sV[t] = vc;
   }
-  const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
-  const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
-  const float hx_2 = a.hx_2, hy_2 = a.hy_2;  // alpha / h^2, divided once on the host (IEEE, same bits)
-  const float wxp = hx_2 * ((x < w - 1) ? 1.f : 0.f), wxm = hx_2 * ((x > 0) ? 1.f : 0.f);
-  const float wyp = hy_2 * ((y < h - 1) ? 1.f : 0.f), wym = hy_2 * ((y > 0) ? 1.f : 0.f);
+  stq<kTinyMax, Q_U>(c.ac, c.uc);
+  stq<kTinyMax, Q_V>(c.ac, c.vc);
+  c.hx2 = a.hx + a.hx; c.hy2 = a.hy + a.hy;
+  c.rhx2 = fast_path_rcp(c.hx2); c.rhy2 = fast_path_rcp(c.hy2);
+  c.wxp = a.hx_2 * ((x < w - 1) ? 1.f : 0.f); c.wxm = a.hx_2 * ((x > 0) ? 1.f : 0.f);
+  c.wyp = a.hy_2 * ((y < h - 1) ? 1.f : 0.f); c.wym = a.hy_2 * ((y > 0) ? 1.f : 0.f);
+  c.e_smooth = a.e_smooth; c.e_data = a.e_data;
+  c.live = on;
 
-  for (int outer = 0; outer < a.outer; ++outer) {
-    if (on) { sDU[t] = du; sDV[t] = dv; }
-    __syncthreads();
-    float phi = 0.f, ksi = 0.f;
-    if (on) {
-      // solve_2d.cu:141-162
-      const float dux = div_rn1(((sU[ir] - sU[il]) + sDU[ir]) - sDU[il], hx2, rhx2);
-      const float duy = div_rn1(((sU[id] - sU[iu]) + sDU[id]) - sDU[iu], hy2, rhy2);
-      const float dvx = div_rn1(((sV[ir] - sV[il]) + sDV[ir]) - sDV[il], hx2, rhx2);
-      const float dvy = div_rn1(((sV[id] - sV[iu]) + sDV[id]) - sDV[iu], hy2, rhy2);
-      float s = duy * duy;
-      s = fmaf(dux, dux, s);
-      s = fmaf(dvx, dvx, s);
-      s = fmaf(dvy, dvy, s);
-      s = fmaf(a.e_smooth, a.e_smooth, s);
-      const float r = sqrtf(s);
-      phi = 1.f / (r + r);
-      // solve_2d.cu:176-196: always the brightness tensor
-      const float j11 = fx * fx, j22 = fy * fy, j12 = fx * fy, j13 = fx * ft, j23 = fy * ft;
-      const float ta = j13 + fmaf(j11, du, j12 * dv);
-      const float tb = j23 + fmaf(j12, du, j22 * dv);
-      const float tc = fmaf(ft, ft, fmaf(j13, du, j23 * dv));
-      float sq = fmaf(du, ta, dv * tb) + tc;
-      sq = sq * ((sq > 0.f) ? 1.f : 0.f);
-      const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
-      ksi = 1.f / (q + q);
-      sPHI[t] = phi;
-    }
-    __syncthreads();
-    float axp = 0.f, axm = 0.f, ayp = 0.f, aym = 0.f, denU = 1.f, denV = 1.f, rU = 0.f, rV = 0.f;
-    if (on) {
-      // solve_2d.cu:333-349, 363, 367
-      axp = wxp * ((sPHI[ir] + phi) * 0.5f);
-      axm = wxm * ((sPHI[il] + phi) * 0.5f);
-      ayp = wyp * ((sPHI[id] + phi) * 0.5f);
-      aym = wym * ((sPHI[iu] + phi) * 0.5f);
-      const float sumH = ((axp + axm) + ayp) + aym;
-      denU = fmaf(J11, ksi, sumH);
-      denV = fmaf(J22, ksi, sumH);
-      rU = fast_path_rcp(denU);
-      rV = fast_path_rcp(denV);
-      sSU[0][t] = uc + du;
-      sSV[0][t] = vc + dv;
-      if (a.phi_out && outer == a.outer - 1) { a.phi_out[g] = phi; a.ksi_out[g] = ksi; }
-    }
-    __syncthreads();
-    for (int k = 0; k < a.sweeps; ++k) {
-      const float* cu = sSU[k & 1];
-      const float* cv = sSV[k & 1];
-      if (on) {
-        // solve_2d.cu:350-367 as compiled: mul, then fma chain xm, xp, yp, ym
-        float sumU = axm * (cu[il] - uc);
-        sumU = fmaf(axp, cu[ir] - uc, sumU);
-        sumU = fmaf(ayp, cu[id] - uc, sumU);
-        sumU = fmaf(aym, cu[iu] - uc, sumU);
-        float sumV = axm * (cv[il] - vc);
-        sumV = fmaf(axp, cv[ir] - vc, sumV);
-        sumV = fmaf(ayp, cv[id] - vc, sumV);
-        sumV = fmaf(aym, cv[iu] - vc, sumV);
-        du = div_rn1(fmaf(ksi, fmaf(nJ12, dv, nJ13), sumU), denU, rU);
-        dv = div_rn1(fmaf(ksi, fmaf(nJ12, du, nJ23), sumV), denV, rV);
-        sSU[(k + 1) & 1][t] = uc + du;
-        sSV[(k + 1) & 1][t] = vc + dv;
-      }
-      __syncthreads();
-    }
+  float phi = 0.f, ksi = 0.f;
+  for (int outer = 0; outer < a.outer; ++outer) one_px_outer<kTinyMax>(c, a.sweeps, du, dv, phi, ksi);
+  if (on) {
+    a.du_out[g] = du; a.dv_out[g] = dv;
+    if (a.phi_out) { a.phi_out[g] = phi; a.ksi_out[g] = ksi; }
   }
-  if (on) { a.du_out[g] = du; a.dv_out[g] = dv; }
 }
 
 bool solve_tiny_fits(int w, int h) { return w >= 2 && h >= 2 && w * h <= kTinyMax; }
@@ -773,99 +815,47 @@ void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad) {
 // of one CTA, and one pixel per thread cuts the dependent chain of a pass by four.  Mask-free like
 // solve_pass: every cell is updated in every sweep, exactness shrinks by one ring per sweep.
 // ---------------------------------------------------------------------------------------------
-// The region edge TS is 32, 24 or 16: the kernel is bound by instruction issue inside the CTA (~760
-// instructions per pixel and pass, one warp per 32 pixels), so a smaller region is a proportionally shorter
-// pass as long as the level's regions still fit the SMs one to one; the scheduler picks the size per level.
+// The region edge TS is 32, 24 or 16: a smaller region is a shorter pass as long as the level's regions
+// still fit the SMs one to one; the scheduler picks the size per level (flow2d_api.cu: run_solve).
 template <bool GRAD, int TS>
 __global__ void __launch_bounds__(TS * TS, 1) solve_small_pass_kernel(const SolveArgs a) {
-  __shared__ float sU[TS * TS], sV[TS * TS], sDU[TS * TS], sDV[TS * TS], sPHI[TS * TS];
-  __shared__ float sSU[2][TS * TS], sSV[2][TS * TS];
+  constexpr int N = TS * TS;
+  __shared__ __align__(16) float sq[kOnePxPlanes * N];
   const int w = a.w, h = a.h;
   const int t = threadIdx.x, ly = t / TS, lx = t - ly * TS;
   const int ox0 = blockIdx.x * a.ow, oy0 = a.y0 + blockIdx.y * a.oh;
   const int ox1 = min(w, ox0 + a.ow), oy1 = min(a.y1, oy0 + a.oh);
   const int gx = ox0 - a.halo_x + lx, gy = oy0 - a.halo_y + ly;
-  const bool inside = gx >= 0 && gx < w && gy >= 0 && gy < h;
   // neighbours inside the region; at the image border the mirrored neighbour is the opposite one; the
   // region's own edge cells have no outer neighbour (they are never exact): any in-range cell will do
   const int il = (gx == 0 || lx == 0) ? t + 1 : t - 1, ir = (gx == w - 1 || lx == TS - 1) ? t - 1 : t + 1;
   const int iu = (gy == 0 || ly == 0) ? t + TS : t - TS, id = (gy == h - 1 || ly == TS - 1) ? t - TS : t + TS;
   const size_t g = (size_t)min(max(gy, 0), h - 1) * a.pitch + min(max(gx, 0), w - 1);
 
-  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;");
-  const float uc = a.u[g], vc = a.v[g], fx = a.fx[g], fy = a.fy[g], ft = a.ft[g];
-  float J11, J22, nJ12, nJ13, nJ23;
+  OnePx c;
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sq);
+  c.ac = base + 4u * t; c.al = base + 4u * il; c.ar = base + 4u * ir; c.au = base + 4u * iu; c.ad = base + 4u * id;
+  asm volatile("griddepcontrol.launch_dependents;");  // the next kernel of the stream may be scheduled (it waits for us)
+  c.uc = a.u[g]; c.vc = a.v[g]; c.fx = a.fx[g]; c.fy = a.fy[g]; c.ft = a.ft[g];
   if (GRAD) {
-    J11 = a.J[0][g]; J22 = a.J[1][g]; nJ12 = -a.J[2][g]; nJ13 = -a.J[3][g]; nJ23 = -a.J[4][g];
+    c.J11 = a.J[0][g]; c.J22 = a.J[1][g]; c.nJ12 = -a.J[2][g]; c.nJ13 = -a.J[3][g]; c.nJ23 = -a.J[4][g];
   } else {
-    J11 = fx * fx; J22 = fy * fy; nJ12 = -(fx * fy); nJ13 = -(fx * ft); nJ23 = -(fy * ft);
+    c.J11 = c.fx * c.fx; c.J22 = c.fy * c.fy; c.nJ12 = -(c.fx * c.fy); c.nJ13 = -(c.fx * c.ft); c.nJ23 = -(c.fy * c.ft);
   }
   if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   float du = 0.f, dv = 0.f;
   if (a.du_in) { du = a.du_in[g]; dv = a.dv_in[g]; }
-  sU[t] = uc; sV[t] = vc; sDU[t] = du; sDV[t] = dv;
-  const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
-  const float rhx2 = fast_path_rcp(hx2), rhy2 = fast_path_rcp(hy2);
-  const float hx_2 = a.hx_2, hy_2 = a.hy_2;  // alpha / h^2, divided once on the host (IEEE, same bits)
-  __syncthreads();
-  // solve_2d.cu:141-162
-  const float dux = div_rn1(((sU[ir] - sU[il]) + sDU[ir]) - sDU[il], hx2, rhx2);
-  const float duy = div_rn1(((sU[id] - sU[iu]) + sDU[id]) - sDU[iu], hy2, rhy2);
-  const float dvx = div_rn1(((sV[ir] - sV[il]) + sDV[ir]) - sDV[il], hx2, rhx2);
-  const float dvy = div_rn1(((sV[id] - sV[iu]) + sDV[id]) - sDV[iu], hy2, rhy2);
-  float s = duy * duy;
-  s = fmaf(dux, dux, s);
-  s = fmaf(dvx, dvx, s);
-  s = fmaf(dvy, dvy, s);
-  s = fmaf(a.e_smooth, a.e_smooth, s);
-  const float rr = sqrtf(s);
-  const float phi = 1.f / (rr + rr);
-  // solve_2d.cu:176-196: always the brightness tensor
-  float ksi;
-  {
-    const float j11 = fx * fx, j22 = fy * fy, j12 = fx * fy, j13 = fx * ft, j23 = fy * ft;
-    const float ta = j13 + fmaf(j11, du, j12 * dv);
-    const float tb = j23 + fmaf(j12, du, j22 * dv);
-    const float tc = fmaf(ft, ft, fmaf(j13, du, j23 * dv));
-    float sq = fmaf(du, ta, dv * tb) + tc;
-    sq = sq * ((sq > 0.f) ? 1.f : 0.f);
-    const float q = sqrtf(fmaf(a.e_data, a.e_data, sq));
-    ksi = inside ? 1.f / (q + q) : 0.f;
-  }
-  sPHI[t] = phi;
-  __syncthreads();
-  // solve_2d.cu:333-349, 363, 367; cells outside the image are inert
-  const float wxp = hx_2 * ((gx < w - 1) ? 1.f : 0.f), wxm = hx_2 * ((gx > 0) ? 1.f : 0.f);
-  const float wyp = hy_2 * ((gy < h - 1) ? 1.f : 0.f), wym = hy_2 * ((gy > 0) ? 1.f : 0.f);
-  float axp = wxp * ((sPHI[ir] + phi) * 0.5f);
-  float axm = wxm * ((sPHI[il] + phi) * 0.5f);
-  float ayp = wyp * ((sPHI[id] + phi) * 0.5f);
-  float aym = wym * ((sPHI[iu] + phi) * 0.5f);
-  const float sumH = ((axp + axm) + ayp) + aym;
-  float denU = fmaf(J11, ksi, sumH), denV = fmaf(J22, ksi, sumH);
-  if (!inside) { axp = axm = ayp = aym = 0.f; denU = denV = 1.f; }
-  const float rU = fast_path_rcp(denU), rV = fast_path_rcp(denV);
-  sSU[0][t] = uc + du;
-  sSV[0][t] = vc + dv;
-  __syncthreads();
-  for (int k = 0; k < a.sweeps; ++k) {
-    const float* cu = sSU[k & 1];
-    const float* cv = sSV[k & 1];
-    // solve_2d.cu:350-367 as compiled: mul, then fma chain xm, xp, yp, ym
-    float sumU = axm * (cu[il] - uc);
-    sumU = fmaf(axp, cu[ir] - uc, sumU);
-    sumU = fmaf(ayp, cu[id] - uc, sumU);
-    sumU = fmaf(aym, cu[iu] - uc, sumU);
-    float sumV = axm * (cv[il] - vc);
-    sumV = fmaf(axp, cv[ir] - vc, sumV);
-    sumV = fmaf(ayp, cv[id] - vc, sumV);
-    sumV = fmaf(aym, cv[iu] - vc, sumV);
-    du = div_rn1(fmaf(ksi, fmaf(nJ12, dv, nJ13), sumU), denU, rU);
-    dv = div_rn1(fmaf(ksi, fmaf(nJ12, du, nJ23), sumV), denV, rV);
-    sSU[(k + 1) & 1][t] = uc + du;
-    sSV[(k + 1) & 1][t] = vc + dv;
-    __syncthreads();
-  }
+  stq<N, Q_U>(c.ac, c.uc);
+  stq<N, Q_V>(c.ac, c.vc);
+  c.hx2 = a.hx + a.hx; c.hy2 = a.hy + a.hy;
+  c.rhx2 = fast_path_rcp(c.hx2); c.rhy2 = fast_path_rcp(c.hy2);
+  c.wxp = a.hx_2 * ((gx < w - 1) ? 1.f : 0.f); c.wxm = a.hx_2 * ((gx > 0) ? 1.f : 0.f);
+  c.wyp = a.hy_2 * ((gy < h - 1) ? 1.f : 0.f); c.wym = a.hy_2 * ((gy > 0) ? 1.f : 0.f);
+  c.e_smooth = a.e_smooth; c.e_data = a.e_data;
+  c.live = gx >= 0 && gx < w && gy >= 0 && gy < h;
+
+  float phi, ksi;
+  one_px_outer<N>(c, a.sweeps, du, dv, phi, ksi);
   if (gx >= ox0 && gx < ox1 && gy >= oy0 && gy < oy1) {
     const size_t o = (size_t)gy * a.pitch + gx;
     a.du_out[o] = du;
