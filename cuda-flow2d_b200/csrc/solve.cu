@@ -684,19 +684,36 @@ struct OnePx {
   bool live;                             // false = the cell is inert (outside the image): zero weights, ksi = 0
 };
 
+// Division in the one-pixel kernels.  Fast variant: the hardware's fast-path sequence with the hoisted
+// reciprocal, WITHOUT a branch; whether every dividend was inside the range where that sequence equals
+// div.rn (or zero, which it also gets right) is accumulated in `ok` and checked once per outer iteration
+// by the whole CTA.  If anything was out of range -- practically never -- the caller repeats the outer
+// iteration with the EXACT variant (plain IEEE divisions).  A per-division branch costs ten control
+// instructions next to three arithmetic ones.
+template <bool EXACT>
+__device__ __forceinline__ float div1(float a, float d, float r, bool& ok) {
+  if (EXACT) return a / d;
+  const float q0 = a * r;
+  const float m = fabsf(a);
+  ok = ok && (m < 0x1p60f) && (m >= 0x1p-60f || m == 0.f);
+  return fmaf(r, fmaf(-d, q0, a), q0);
+}
+
 // One outer iteration: publish du, dv; phi, ksi; weights; `sweeps` Jacobi sweeps.  The caller has put uc, vc
 // into planes Q_U, Q_V.  Ends with a barrier.  Same operations, in the same order, as solve_pass.
-template <int N>
-__device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, float& du, float& dv, float& phi, float& ksi) {
+// Returns false (to every thread of the CTA alike) if the fast divisions were not safe somewhere.
+template <int N, bool EXACT>
+__device__ __forceinline__ bool one_px_outer_impl(const OnePx& c, int sweeps, float& du, float& dv, float& phi, float& ksi) {
+  bool ok = c.rhx2 != 0.f && c.rhy2 != 0.f;
   stq<N, Q_DU>(c.ac, du);
   stq<N, Q_DV>(c.ac, dv);
   __syncthreads();
   {
     // solve_2d.cu:141-162
-    const float dux = div_rn1(((ldq<N, Q_U>(c.ar) - ldq<N, Q_U>(c.al)) + ldq<N, Q_DU>(c.ar)) - ldq<N, Q_DU>(c.al), c.hx2, c.rhx2);
-    const float duy = div_rn1(((ldq<N, Q_U>(c.ad) - ldq<N, Q_U>(c.au)) + ldq<N, Q_DU>(c.ad)) - ldq<N, Q_DU>(c.au), c.hy2, c.rhy2);
-    const float dvx = div_rn1(((ldq<N, Q_V>(c.ar) - ldq<N, Q_V>(c.al)) + ldq<N, Q_DV>(c.ar)) - ldq<N, Q_DV>(c.al), c.hx2, c.rhx2);
-    const float dvy = div_rn1(((ldq<N, Q_V>(c.ad) - ldq<N, Q_V>(c.au)) + ldq<N, Q_DV>(c.ad)) - ldq<N, Q_DV>(c.au), c.hy2, c.rhy2);
+    const float dux = div1<EXACT>(((ldq<N, Q_U>(c.ar) - ldq<N, Q_U>(c.al)) + ldq<N, Q_DU>(c.ar)) - ldq<N, Q_DU>(c.al), c.hx2, c.rhx2, ok);
+    const float duy = div1<EXACT>(((ldq<N, Q_U>(c.ad) - ldq<N, Q_U>(c.au)) + ldq<N, Q_DU>(c.ad)) - ldq<N, Q_DU>(c.au), c.hy2, c.rhy2, ok);
+    const float dvx = div1<EXACT>(((ldq<N, Q_V>(c.ar) - ldq<N, Q_V>(c.al)) + ldq<N, Q_DV>(c.ar)) - ldq<N, Q_DV>(c.al), c.hx2, c.rhx2, ok);
+    const float dvy = div1<EXACT>(((ldq<N, Q_V>(c.ad) - ldq<N, Q_V>(c.au)) + ldq<N, Q_DV>(c.ad)) - ldq<N, Q_DV>(c.au), c.hy2, c.rhy2, ok);
     float s = duy * duy;
     s = fmaf(dux, dux, s);
     s = fmaf(dvx, dvx, s);
@@ -724,7 +741,8 @@ __device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, float& 
   const float sumH = ((axp + axm) + ayp) + aym;
   float denU = fmaf(c.J11, ksi, sumH), denV = fmaf(c.J22, ksi, sumH);
   if (!c.live) { axp = axm = ayp = aym = 0.f; denU = denV = 1.f; }
-  const float rU = fast_path_rcp(denU), rV = fast_path_rcp(denV);
+  const float rU = EXACT ? 0.f : fast_path_rcp(denU), rV = EXACT ? 0.f : fast_path_rcp(denV);
+  ok = ok && (EXACT || (rU != 0.f && rV != 0.f));
   const float uc = c.uc, vc = c.vc;
   stq<N, Q_SU0>(c.ac, uc + du);
   stq<N, Q_SV0>(c.ac, vc + dv);
@@ -741,8 +759,8 @@ __device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, float& 
     sumV = fmaf(axp, ldq<N, CV>(c.ar) - vc, sumV);
     sumV = fmaf(ayp, ldq<N, CV>(c.ad) - vc, sumV);
     sumV = fmaf(aym, ldq<N, CV>(c.au) - vc, sumV);
-    du = div_rn1(fmaf(ksi, fmaf(c.nJ12, dv, c.nJ13), sumU), denU, rU);
-    dv = div_rn1(fmaf(ksi, fmaf(c.nJ12, du, c.nJ23), sumV), denV, rV);
+    du = div1<EXACT>(fmaf(ksi, fmaf(c.nJ12, dv, c.nJ13), sumU), denU, rU, ok);
+    dv = div1<EXACT>(fmaf(ksi, fmaf(c.nJ12, du, c.nJ23), sumV), denV, rV, ok);
     stq<N, NU>(c.ac, uc + du);
     stq<N, NV>(c.ac, vc + dv);
     __syncthreads();
@@ -750,6 +768,18 @@ __device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, float& 
   for (int k = 0; k < sweeps; k += 2) {
     sweep(std::true_type{});
     if (k + 1 < sweeps) sweep(std::false_type{});
+  }
+  if (EXACT) return true;
+  return __syncthreads_or(!ok) == 0;
+}
+
+template <int N>
+__device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, float& du, float& dv, float& phi, float& ksi) {
+  const float du0 = du, dv0 = dv;
+  if (!one_px_outer_impl<N, false>(c, sweeps, du, dv, phi, ksi)) {
+    du = du0;
+    dv = dv0;
+    one_px_outer_impl<N, true>(c, sweeps, du, dv, phi, ksi);
   }
 }
 
