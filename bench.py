@@ -258,7 +258,11 @@ def run_ours(args, wl, rank, world, local_rank):
     handles = [m.Flow2D(w, h, constancy=m.GRADIENT if wl.get("gradient") else m.GREY, device=dev) for _ in range(K)]
     fl = handles[0]
     params = m.default_params(**cfg)
-    params.throughput_mode = 1 if K > 1 else 0  # several handles share the GPU: redundant halo work is not free
+    # (flow2d_params.throughput_mode = 1 used to pay off for several handles per GPU; with the final one-pixel kernels
+    # the latency schedule is also the better throughput schedule -- profiles/r01/README.md -- so it stays 0)
+    params.throughput_mode = 0
+    if os.environ.get("FLOW2D_BENCH_THROUGHPUT_MODE") is not None:  # A/B switch for measurements
+        params.throughput_mode = int(os.environ["FLOW2D_BENCH_THROUGHPUT_MODE"])
     base = torch.cuda.Stream(device=dev)
     streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
     for hd, st in zip(handles, streams):

@@ -142,8 +142,9 @@ int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, 
   const int K = std::max(1, std::min(opt.handles, n_pairs));
   const int R = K + 3, M = 2 * K;
 
+  // (throughput_mode stays as the caller set it: measured on B200 with 4-8 handles, the latency schedule of the
+  // one-pixel kernels is also the better throughput schedule)
   flow2d_params p = opt.params;
-  if (K > 1) p.throughput_mode = 1;  // the GPU is shared: schedule for throughput, not for latency
 
   std::vector<flow2d_handle*> handles(K, nullptr);
   auto destroy_handles = [&]() {

@@ -66,9 +66,10 @@ typedef struct flow2d_params {
   int    sweeps_per_pass;        /* Jacobi sweeps fused into one solve_pass launch (1..FLOW2D_MAX_SWEEPS_PER_PASS) */
   int    resident_levels;        /* 0 auto (one-thread-per-pixel CTA for levels <= 1024 px, resident solve_pass CTA for
                                     levels <= 59x46, tiled passes otherwise) / 2 = no one-thread-per-pixel kernels / -1 = always tiled */
-  int    throughput_mode;        /* 0 = schedule for the latency of ONE frame pair (mid-size levels use the one-thread-per-
-                                    pixel pass, which trades redundant halo work for a 3x shorter dependent chain);
-                                    1 = schedule for throughput: several handles share the GPU, redundant work is not free */
+  int    throughput_mode;        /* 0 (default) = mid-size levels use the one-thread-per-pixel pass, which trades redundant halo
+                                    work for a 3x shorter dependent chain; 1 = they use 64x48 tiles / the resident CTA (least
+                                    SM time).  Measured on B200 with the kernels of round 1, 0 is faster for one frame pair AND
+                                    for 4-8 handles sharing the GPU; 1 is kept for many handles on a saturated GPU */
   int    report_residuals;       /* opt-in diagnostics (no reference counterpart, see flow2d_level_residuals): 1 = record
                                     the residual norm of every level's last linear system; results are unchanged */
 } flow2d_params;
