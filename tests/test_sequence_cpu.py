@@ -71,3 +71,39 @@ def test_bad_inputs_exit_2_like_unreadable_frames(frames):
     assert _list(["dir32", "--u8"], frames)[0] == 2                      # forced type does not match the sizes
     (frames / "empty").mkdir()
     assert _list(["empty"], frames)[0] == 2
+
+
+def _cli(args, cwd):
+    r = subprocess.run([CLI] + [str(a) for a in args], cwd=cwd, stdin=subprocess.DEVNULL, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=60)
+    return r.returncode, r.stdout.decode()
+
+
+def test_cli_exit_codes_that_need_no_gpu(tmp_path):
+    """Same exit codes as the reference command line for the paths it decides before touching CUDA
+    (src/main.cpp:99-160): 3 = settings unreadable, 0 = usage."""
+    assert _cli(["missing.xml"], tmp_path)[0] == 3
+    (tmp_path / "broken.xml").write_text("<Settings><Input><Path inputPath='x'/></Input></Settings>")  # required elements missing
+    rc, out = _cli(["broken.xml"], tmp_path)
+    assert rc == 3 and "missing" in out
+    assert _cli(["a", "b", "c"], tmp_path)[0] == 0                 # wrong argument count: usage text
+    rc, out = _cli(["--sequence", 40, 30], tmp_path)
+    assert rc == 0 and "Usage" in out
+    rc, out = _cli(["--sequence", 40, 30, "out/", "x.raw", "--bogus"], tmp_path)
+    assert rc == 0 and "Unknown option" in out
+    rc, out = _cli(["--sequence", 40, 30, "out/", "--settings", "missing.xml", "x.raw", "y.raw"], tmp_path)
+    assert rc == 3
+
+
+def test_settings_file_of_the_reference_schema_is_accepted(tmp_path, frames):
+    """The reference's settings.xml schema (settings.xml:1-27) with 8-bit frames, through --sequence --settings --list
+    (no GPU needed up to the listing)."""
+    (frames / "s.xml").write_text(
+        '<?xml version="1.0" ?>\n<Settings>\n  <Input>\n    <Path inputPath="./dir8/" />\n'
+        '    <Mode Nx="40" Ny="30" imageType="8-bit">\n      <Files file1="f00.raw" file2="f01.raw" />\n    </Mode>\n  </Input>\n'
+        '  <Parameters>\n    <Method key="false" />\n    <Solver>\n      <Iterations inner="5" outer="20" />\n'
+        '      <Warping levels="20" scaling="0.9" medianRadius="5" />\n'
+        '      <Model sigma="0.45" alpha="3.5" e_smooth="0.001" e_data="0.001" />\n    </Solver>\n  </Parameters>\n'
+        '  <Output>\n    <Path outputPath="./out/" />\n  </Output>\n</Settings>\n')
+    rc, out = _list(["dir8", "--settings", "s.xml"], frames)
+    assert rc == 0 and "8 frames of 40x30 (directory, 8-bit)" in out
