@@ -64,8 +64,9 @@ typedef struct flow2d_params {
   float  gaussian_sigma;         /* "gaussian_sigma"         settings.xml Model@sigma; <= 0 = off */
   /* scheduling (0 = automatic); results are identical for every value */
   int    sweeps_per_pass;        /* Jacobi sweeps fused into one solve_pass launch (1..FLOW2D_MAX_SWEEPS_PER_PASS) */
-  int    resident_levels;        /* 0 auto (one-thread-per-pixel CTA for levels <= 1024 px, resident solve_pass CTA for
-                                    levels <= 59x46, tiled passes otherwise) / 2 = no one-thread-per-pixel kernels / -1 = always tiled */
+  int    resident_levels;        /* 0 auto (whole-level one-thread-per-pixel CTA for levels <= 1024 px, one-thread-per-pixel passes
+                                    or 64x48 tiles above, chosen per level by a time model) / 2 = no one-thread-per-pixel kernels
+                                    (levels <= 59x46 run in one resident solve_pass CTA) / -1 = always tiled */
   int    throughput_mode;        /* 0 (default) = mid-size levels use the one-thread-per-pixel pass, which trades redundant halo
                                     work for a 3x shorter dependent chain; 1 = they use 64x48 tiles / the resident CTA (least
                                     SM time).  Measured on B200 with the kernels of round 1, 0 is faster for one frame pair AND
