@@ -67,3 +67,35 @@ def test_product_does_not_touch_the_oracle():
                 if re.search(r"liboracle|flow2d_oracle|from oracle|import oracle|oracle/", t):
                     bad.append(os.path.join(base, f))
     assert not bad, bad
+
+
+def test_level_table_random_sizes(pkg, oracle):
+    """Randomised: flow2d_max_warp_level / flow2d_level_geometry (host-only fp32 arithmetic of
+    optical_flow_base_2d.cpp:36-59, optical_flow_2d.cpp:268-272) agree with the oracle for any size and scale."""
+    rng = np.random.default_rng(42)
+    for _ in range(300):
+        W, H = int(rng.integers(4, 9000)), int(rng.integers(4, 9000))
+        sf = float(np.float32(rng.uniform(0.3, 0.97)))
+        assert pkg.max_warp_level(W, H, sf) == oracle.max_warp_level(W, H, sf), (W, H, sf)
+        a, b = pkg.level_table(W, H, sf, 1000), oracle.level_table(W, H, sf, 1000)
+        assert len(a) == len(b) and all(x[:2] == y[:2] and x[2].tobytes() == y[2].tobytes() and x[3].tobytes() == y[3].tobytes()
+                                        for x, y in zip(a, b)), (W, H, sf)
+
+
+def test_null_handle_is_an_error_not_a_crash(pkg):
+    """Every entry point that takes a handle answers FLOW2D_ERR_INVALID_ARGUMENT (-1) for NULL (the reference
+    dereferences uninitialised operation pointers in that situation)."""
+    import ctypes as C
+    L = pkg.binding.lib() if hasattr(pkg, "binding") else None
+    if L is None:
+        from cuda_flow2d_b200 import binding
+        L = binding.lib()
+    null = C.c_void_p(0)
+    p = pkg.default_params()
+    assert L.flow2d_compute(null, null, null, null, null, C.byref(p)) == -1
+    assert L.flow2d_compute_device(null, null, null, null, null, C.byref(p)) == -1
+    assert L.flow2d_synchronize(null) == -1
+    assert L.flow2d_set_stream(null, null) == -1
+    assert L.flow2d_last_launch_counts(null, None) == -1
+    assert L.flow2d_pitch_elems(null) == 0 and L.flow2d_width(null) == 0
+    assert L.flow2d_destroy(null) == 0  # destroying nothing is fine
