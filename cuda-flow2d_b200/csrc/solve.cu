@@ -699,6 +699,28 @@ __device__ __forceinline__ float div1(float a, float d, float r, bool& ok) {
   return fmaf(r, fmaf(-d, q0, a), q0);
 }
 
+// sqrt.rn / rcp.rn the same way: the compiler's own fast-path sequences (MUFU.RSQ / MUFU.RCP + the Newton
+// step it emits for sqrtf and 1.f/x on sm_100) without their range branch; arguments outside 2^-100 .. 2^100
+// (inside the range where those sequences ARE sqrt.rn / rcp.rn) clear `ok`.  Arguments here are positive.
+template <bool EXACT>
+__device__ __forceinline__ float sqrt1(float x, bool& ok) {
+  if (EXACT) return sqrtf(x);
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  const float s = x * y, hh = y * 0.5f;
+  ok = ok && x >= 0x1p-100f && x < 0x1p100f;
+  return fmaf(fmaf(-s, s, x), hh, s);
+}
+template <bool EXACT>
+__device__ __forceinline__ float rcp1(float x, bool& ok) {
+  if (EXACT) return 1.f / x;
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(x));
+  const float e = -fmaf(x, r0, -1.f);
+  ok = ok && x >= 0x1p-100f && x < 0x1p100f;
+  return fmaf(r0, e, r0);
+}
+
 // One outer iteration: publish du, dv; phi, ksi; weights; `sweeps` Jacobi sweeps.  The caller has put uc, vc
 // into planes Q_U, Q_V.  Ends with a barrier.  Same operations, in the same order, as solve_pass.
 // Returns false (to every thread of the CTA alike) if the fast divisions were not safe somewhere.
@@ -719,8 +741,8 @@ __device__ __forceinline__ bool one_px_outer_impl(const OnePx& c, int sweeps, fl
     s = fmaf(dvx, dvx, s);
     s = fmaf(dvy, dvy, s);
     s = fmaf(c.e_smooth, c.e_smooth, s);
-    const float rr = sqrtf(s);
-    phi = 1.f / (rr + rr);
+    const float rr = sqrt1<EXACT>(s, ok);
+    phi = rcp1<EXACT>(rr + rr, ok);
     // solve_2d.cu:176-196: always the brightness tensor
     const float j11 = c.fx * c.fx, j22 = c.fy * c.fy, j12 = c.fx * c.fy, j13 = c.fx * c.ft, j23 = c.fy * c.ft;
     const float ta = j13 + fmaf(j11, du, j12 * dv);
@@ -728,8 +750,9 @@ __device__ __forceinline__ bool one_px_outer_impl(const OnePx& c, int sweeps, fl
     const float tc = fmaf(c.ft, c.ft, fmaf(j13, du, j23 * dv));
     float sq = fmaf(du, ta, dv * tb) + tc;
     sq = sq * ((sq > 0.f) ? 1.f : 0.f);
-    const float q = sqrtf(fmaf(c.e_data, c.e_data, sq));
-    ksi = c.live ? 1.f / (q + q) : 0.f;
+    const float q = sqrt1<EXACT>(fmaf(c.e_data, c.e_data, sq), ok);
+    const float rq = rcp1<EXACT>(q + q, ok);
+    ksi = c.live ? rq : 0.f;
   }
   stq<N, Q_PHI>(c.ac, phi);
   __syncthreads();
