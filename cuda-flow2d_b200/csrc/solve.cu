@@ -24,12 +24,16 @@
 // x neighbours by warp shuffle, y neighbours through double-buffered shared planes, one
 // __syncthreads per sweep.
 //
-//   phase A  all global loads of the pass (float4 per strip); motion tensor and ksi -> planes
+//   phase A  the loads of the pass: planes that are only handed over or published go global -> shared by
+//            cp.async; a first pass of an outer iteration loads fx, fy, ft, du, dv into registers and
+//            computes ksi
 //   phase B  u/v/du/dv published for the neighbour rows; phi
-//            (or phi/ksi of an earlier pass of the same outer iteration are loaded)
-//   phase C  edge weights, sumH, the two denominators and their fast-path reciprocals
-//   phase D  S Jacobi sweeps
+//            (skipped when phi/ksi of an earlier pass of the same outer iteration were staged by phase A)
+//   phase C  motion tensor, edge weights, sumH, the two denominators and their fast-path reciprocals
+//   phase D  S Jacobi sweeps (unrolled by buffer parity; PTX ld/st.shared with immediate plane offsets)
 //   phase E  store du, dv of the output tile
+//
+// Mid-size and tiny levels use the one-pixel-per-thread kernels further down (solve_small_pass, solve_tiny).
 //
 // "Resident" mode: if the whole level fits one region, a single CTA runs ALL outer iterations and
 // all inner sweeps of the level without leaving the SM (grid = 1).
