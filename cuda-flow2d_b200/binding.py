@@ -78,6 +78,7 @@ def lib():
         L.flow2d_synchronize.argtypes = [vp]
         L.flow2d_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_int), fp]
         L.flow2d_last_launch_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.flow2d_graph_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         dp = C.POINTER(C.c_double)
         L.flow2d_level_residuals.argtypes = [vp, dp, dp, C.c_int, C.POINTER(C.c_int)]
         L.flow2d_stage_residual.argtypes = [vp] + [vp] * 8 + [C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.POINTER(Params), dp, dp]
@@ -172,6 +173,12 @@ class Flow2D:
         n, lv, ms = C.c_longlong(), C.c_int(), C.c_float()
         self._check(lib().flow2d_last_stats(self._h, C.byref(n), C.byref(lv), C.byref(ms)))
         return {"kernel_launches": n.value, "levels_run": lv.value, "device_ms": ms.value}
+
+    def graph_stats(self):
+        """(captures, replays) of the handle's CUDA-graph cache since it was created (flow2d_graph_stats)."""
+        a, b = C.c_longlong(), C.c_longlong()
+        self._check(lib().flow2d_graph_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def level_residuals(self):
         """(rms_u, rms_v) per level of the last compute with params.report_residuals = 1, coarsest level first."""

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <initializer_list>
 #include <string>
 
 #include "../../include/flow2d.h"
@@ -54,12 +55,22 @@ struct flow2d_handle {
   int levels_run = 0;
   float device_ms = 0.f;
   unsigned long long* timing = nullptr;  // debug: phase stamps of solve_pass (flow2d_debug_timing)
-  cudaGraphExec_t graph_exec = nullptr;  // captured level schedule of the last (buffers, parameters) combination
-  unsigned char graph_key[128] = {};
-  long long graph_launches = 0;
-  int graph_residual_levels = 0;
-  long long graph_kind_launches[FLOW2D_KERNEL_KINDS] = {};
-  int graph_levels = 0;
+  // captured level schedules, one per (buffers, parameters) combination, least recently used one evicted:
+  // a caller that rotates a few frame / flow containers (a frame ring, several pairs per handle) replays
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    unsigned char key[128] = {};
+    long long launches = 0;
+    long long kind_launches[FLOW2D_KERNEL_KINDS] = {};
+    int levels = 0, residual_levels = 0;
+    int residual_px[FLOW2D_MAX_LEVELS] = {};
+    unsigned long long last_use = 0;
+  };
+  static constexpr int kGraphSlots = 8;
+  GraphEntry graphs[kGraphSlots];
+  unsigned long long graph_clock = 0;
+  long long graph_captures = 0, graph_replays = 0;
+  int sm_count = 148;
   std::string err;
 };
 
@@ -147,6 +158,14 @@ int normalise_median(flow2d_handle* h, size_t radius, int* out) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Every kernel addresses containers with float4 loads / stores: a caller pointer that is only 4-byte aligned (a
+// sub-view of a larger buffer) must be refused here, not fault on the device.
+int check_aligned(flow2d_handle* h, const char* stage, std::initializer_list<const void*> ptrs) {
+  for (const void* q : ptrs)
+    if (!aligned16(q)) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "%s: device containers must be 16-byte aligned", stage);
+  return FLOW2D_OK;
+}
+
 int check_level(flow2d_handle* h, size_t w, size_t hh) {
   if (w < 2 || hh < 2 || w > h->W || hh > h->H)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "level size %zux%zu outside [2x2, %zux%zu]", w, hh, h->W, h->H);
@@ -185,6 +204,10 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   a.hy_2 = a.alpha / (a.hy * a.hy);
   a.timing = h->timing;
   a.y0 = 0; a.y1 = g.h;
+  // e_smooth = 0 or e_data = 0 (legal) makes the argument of sqrt exactly zero on every flat cell, outside the range
+  // the branch-free sqrt / rcp of the one-pixel kernels cover: take their plain IEEE variant from the start instead of
+  // computing every outer iteration twice
+  a.exact = (a.e_smooth * a.e_smooth < 0x1p-100f || a.e_data * a.e_data < 0x1p-100f) ? 1 : 0;
 
   // tiny levels (<= 1024 pixels): one CTA, one thread per pixel, all outer iterations in the kernel
   if (p->resident_levels >= 0 && p->resident_levels != 2 && solve_tiny_fits(g.w, g.h)) {
@@ -226,7 +249,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
     for (int s = 1; s <= FLOW2D_MAX_SWEEPS_PER_PASS; ++s) {
       const int np = (inner + s - 1) / s;
       const int ow = kSolveLW - 2 * ((s + 1 <= 4) ? 4 : 8), oh = kSolveLH - 2 * (s + 1);
-      double waves = (double)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) / 148.0;
+      double waves = (double)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) / (double)h->sm_count;
       if (waves < 1.0) waves = 1.0;
       const double cost = waves * (11.0 + (np - 1) * 7.5 + 0.85 * inner);
       if (cost < best) { best = cost; S = s; }
@@ -316,14 +339,15 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       bool small = false;
       if (npass == 1 && p->resident_levels != 2 && p->resident_levels != -1 && !p->throughput_mode) {
         const long long n_big = (long long)((g.w + a.ow - 1) / a.ow) * ((vb - va + a.oh - 1) / a.oh);
-        double t_best = 0.7 + 11.1 * (n_big > 148 ? (double)n_big / 148.0 : 1.0);
+        const long long sms = h->sm_count;
+        double t_best = 0.7 + 11.1 * (n_big > sms ? (double)n_big / (double)sms : 1.0);
         int ts_best = 0;
         static const int kRegion[3] = {32, 24, 16};
         for (int ts : kRegion) {
           const int so = ts - 2 * (s + 1);
           if (so < 4) continue;
           const long long n = (long long)((g.w + so - 1) / so) * ((vb - va + so - 1) / so);
-          const double t = 1.0 + (double)((n + 147) / 148) * (2.5 + 1.6 * (ts * ts) / 1024.0);
+          const double t = 1.0 + (double)((n + sms - 1) / sms) * (2.5 + 1.6 * (ts * ts) / 1024.0);
           if (t < t_best) { t_best = t; ts_best = ts; }
         }
         if (ts_best) {
@@ -496,17 +520,20 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   key.p.throughput_mode = p->throughput_mode;
   key.p.report_residuals = p->report_residuals;
   key.timing = h->timing;
-  if (h->graph_exec && std::memcmp(&key, h->graph_key, sizeof key) == 0) {
-    CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
-    h->launches = h->graph_launches;
-    for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) h->kind_launches[k] = h->graph_kind_launches[k];
-    h->levels_run = h->graph_levels;
-    h->residual_levels = h->graph_residual_levels;
+  static_assert(sizeof(GraphKey) <= sizeof(h->graphs[0].key), "graph key storage too small");
+  flow2d_handle::GraphEntry* slot = nullptr;
+  for (auto& g : h->graphs)
+    if (g.exec && std::memcmp(&key, g.key, sizeof key) == 0) slot = &g;
+  if (slot) {
+    CU_TRY(h, cudaGraphLaunch(slot->exec, h->stream));
+    slot->last_use = ++h->graph_clock;
+    ++h->graph_replays;
+    h->launches = slot->launches;
+    for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) h->kind_launches[k] = slot->kind_launches[k];
+    h->levels_run = slot->levels;
+    h->residual_levels = slot->residual_levels;
+    std::memcpy(h->residual_px, slot->residual_px, sizeof h->residual_px);
     return FLOW2D_OK;
-  }
-  if (h->graph_exec) {
-    cudaGraphExecDestroy(h->graph_exec);
-    h->graph_exec = nullptr;
   }
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     (void)cudaGetLastError();
@@ -529,14 +556,24 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
     return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
   }
   cudaGraphDestroy(graph);
-  h->graph_exec = exec;
-  static_assert(sizeof(GraphKey) <= sizeof(h->graph_key), "graph key storage too small");
-  std::memcpy(h->graph_key, &key, sizeof key);
-  h->graph_launches = h->launches;
-  for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) h->graph_kind_launches[k] = h->kind_launches[k];
-  h->graph_levels = h->levels_run;
-  h->graph_residual_levels = h->residual_levels;
-  CU_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
+  // a free slot, else the least recently used one (its graph may still be executing: destroying an exec that is
+  // in flight is allowed, the driver defers the release)
+  slot = &h->graphs[0];
+  for (auto& g : h->graphs) {
+    if (!g.exec) { slot = &g; break; }
+    if (g.last_use < slot->last_use) slot = &g;
+  }
+  if (slot->exec) cudaGraphExecDestroy(slot->exec);
+  slot->exec = exec;
+  std::memcpy(slot->key, &key, sizeof key);
+  slot->launches = h->launches;
+  for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) slot->kind_launches[k] = h->kind_launches[k];
+  slot->levels = h->levels_run;
+  slot->residual_levels = h->residual_levels;
+  std::memcpy(slot->residual_px, h->residual_px, sizeof h->residual_px);
+  slot->last_use = ++h->graph_clock;
+  ++h->graph_captures;
+  CU_TRY(h, cudaGraphLaunch(slot->exec, h->stream));
   return FLOW2D_OK;
 }
 
@@ -628,6 +665,7 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
   flow2d_handle* h = new (std::nothrow) flow2d_handle;
   if (!h) return FLOW2D_ERR_OUT_OF_MEMORY;
   h->device = device;
+  h->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   h->W = width; h->H = height;
   h->pitch = (width + kPitchAlign - 1) / kPitchAlign * kPitchAlign;
   h->constancy = constancy;
@@ -665,7 +703,8 @@ int flow2d_destroy(flow2d_handle* h) {
   if (!h) return FLOW2D_OK;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -695,6 +734,13 @@ int flow2d_last_stats(const flow2d_handle* h, long long* kernel_launches, int* l
   return FLOW2D_OK;
 }
 
+int flow2d_graph_stats(const flow2d_handle* h, long long* captures, long long* replays) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  if (captures) *captures = h->graph_captures;
+  if (replays) *replays = h->graph_replays;
+  return FLOW2D_OK;
+}
+
 int flow2d_level_residuals(flow2d_handle* h, double* rms_u, double* rms_v, int capacity, int* levels) {
   STAGE_PROLOGUE(h);
   if (levels) *levels = h->residual_levels;
@@ -716,6 +762,7 @@ int flow2d_stage_residual(flow2d_handle* h, const float* d_frame_0, const float*
   if (!d_frame_0 || !d_frame_1_warped || !d_u || !d_v || !d_du || !d_dv || !d_phi || !d_ksi || !p)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null pointer");
   if (w < 2 || hh < 2 || w > h->W || hh > h->H) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "level %zux%zu does not fit the handle", w, hh);
+  TRY(check_aligned(h, "residual", {d_frame_0, d_frame_1_warped, d_u, d_v, d_du, d_dv, d_phi, d_ksi}));
   const LevelGeom g = geom(h, w, hh, hx, hy);
   TRY(run_derivatives(h, g, d_frame_0, d_frame_1_warped));
   CU_TRY(h, cudaMemsetAsync(h->d_residuals, 0, sizeof(double) * 2, h->stream));
@@ -799,6 +846,7 @@ int flow2d_compute_slab_device(flow2d_handle* h, const float* d_frame_0, const f
   if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null image pointer");
   if (!slab || slab->world < 1 || slab->rank < 0 || slab->rank >= slab->world || (slab->world > 1 && !slab->exchange))
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "bad slab description");
+  TRY(check_aligned(h, "compute", {d_frame_0, d_frame_1, d_flow_u, d_flow_v}));
   CU_TRY(h, cudaSetDevice(h->device));
   reset_launch_counts(h);
   return enqueue_pyramid(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p, slab);  // callbacks inside: no graph capture
@@ -815,6 +863,7 @@ int flow2d_stage_solve_slab(flow2d_handle* h, const float* d_frame_0, const floa
   if (p->sweeps_per_pass < 0 || p->sweeps_per_pass > FLOW2D_MAX_SWEEPS_PER_PASS)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "sweeps_per_pass must be 0..%d", FLOW2D_MAX_SWEEPS_PER_PASS);
   TRY(check_level(h, w, hh));
+  TRY(check_aligned(h, "solve", {d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_flow_du, d_flow_dv}));
   const LevelGeom g = geom(h, w, hh, hx, hy);
   TRY(run_derivatives(h, g, d_frame_0, d_frame_1));
   return run_solve(h, g, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI],
@@ -835,6 +884,7 @@ int flow2d_stage_blur(flow2d_handle* h, const float* d_in, float* d_out, size_t 
   STAGE_PROLOGUE(h);
   if (!d_in || !d_out || d_in == d_out) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "blur: bad buffers (in-place is refused)");
   TRY(check_level(h, w, hh));
+  TRY(check_aligned(h, "blur", {d_in, d_out}));
   GaussTaps taps;
   TRY(gauss_taps(h, sigma, &taps));
   launch_blur(h->stream, d_in, d_out, (int)w, (int)hh, (int)h->pitch, taps);
@@ -846,6 +896,7 @@ int flow2d_stage_resample(flow2d_handle* h, const float* d_in, size_t iw, size_t
   if (!d_in || !d_out || d_in == d_out) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "resample: bad buffers (in-place is refused)");
   if (iw < 1 || ih < 1 || ow < 1 || oh < 1 || iw > h->W || ow > h->W || ih > h->H || oh > h->H)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "resample: size outside the container");
+  TRY(check_aligned(h, "resample", {d_in, d_out}));
   const float* in[2] = {d_in, d_in};
   float* tmp[2] = {h->c[C_TMP0], h->c[C_TMP0]};
   float* out[2] = {d_out, d_out};
@@ -859,6 +910,7 @@ int flow2d_stage_warp(flow2d_handle* h, const float* d_frame_0, const float* d_f
   if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v || !d_out || d_out == d_frame_1 || d_out == d_frame_0)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "warp: bad buffers (in-place is refused)");
   TRY(check_level(h, w, hh));
+  TRY(check_aligned(h, "warp", {d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_out}));
   launch_warp(h->stream, d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_out, geom(h, w, hh, hx, hy));
   return check_launch(h, FLOW2D_K_WARP, 1);
 }
@@ -887,6 +939,7 @@ int flow2d_stage_add(flow2d_handle* h, float* d_a, const float* d_b, size_t w, s
   STAGE_PROLOGUE(h);
   if (!d_a || !d_b) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "add: null buffer");
   TRY(check_level(h, w, hh));
+  TRY(check_aligned(h, "add", {d_a, d_b}));
   launch_add(h->stream, d_a, d_b, (int)w, (int)hh, (int)h->pitch);
   return check_launch(h, FLOW2D_K_ADD, 1);
 }
@@ -897,6 +950,7 @@ int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b
   if (!d_a || !d_out || d_a == d_out || d_b == d_out)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "median: bad buffers (in-place is refused)");
   TRY(check_level(h, w, hh));
+  TRY(check_aligned(h, "median", {d_a, d_b, d_out}));
   int r = 1;
   TRY(normalise_median(h, radius, &r));
   const float* a[2] = {d_a, d_a};

@@ -49,6 +49,7 @@ struct SolveArgs {
   int halo_x, halo_y;             // region origin = tile origin - halo; halo_x % 4 == 0
   int y0, y1;                     // rows of the level this launch produces (0, h unless the level is slabbed)
   unsigned long long* timing;     // debug: 8 globaltimer stamps per CTA (null = off)
+  int exact;                      // one-pixel kernels: 1 = plain IEEE div / sqrt / rcp from the start (see one_px_outer)
   int pdl;                        // 1 = launched with programmatic stream serialization: the previous kernel on the
                                   // stream is the previous pass of this solve (it writes only du/dv/phi/ksi)
 };

@@ -797,13 +797,13 @@ __device__ __forceinline__ bool one_px_outer_impl(const OnePx& c, int sweeps, fl
     if (k + 1 < sweeps) sweep(std::false_type{});
   }
   if (EXACT) return true;
-  return __syncthreads_or(!ok) == 0;
+  return __syncthreads_or(c.live && !ok) == 0;  // what an inert cell (outside the image) computes is never used
 }
 
 template <int N>
-__device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, float& du, float& dv, float& phi, float& ksi) {
+__device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, bool exact, float& du, float& dv, float& phi, float& ksi) {
   const float du0 = du, dv0 = dv;
-  if (!one_px_outer_impl<N, false>(c, sweeps, du, dv, phi, ksi)) {
+  if (exact || !one_px_outer_impl<N, false>(c, sweeps, du, dv, phi, ksi)) {
     du = du0;
     dv = dv0;
     one_px_outer_impl<N, true>(c, sweeps, du, dv, phi, ksi);
@@ -849,7 +849,7 @@ __global__ void __launch_bounds__(kTinyMax, 1) solve_tiny_kernel(const SolveArgs
   c.live = on;
 
   float phi = 0.f, ksi = 0.f;
-  for (int outer = 0; outer < a.outer; ++outer) one_px_outer<kTinyMax>(c, a.sweeps, du, dv, phi, ksi);
+  for (int outer = 0; outer < a.outer; ++outer) one_px_outer<kTinyMax>(c, a.sweeps, a.exact != 0, du, dv, phi, ksi);
   if (on) {
     a.du_out[g] = du; a.dv_out[g] = dv;
     if (a.phi_out) { a.phi_out[g] = phi; a.ksi_out[g] = ksi; }
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(TS * TS, 1) solve_small_pass_kernel(const Solv
   c.live = gx >= 0 && gx < w && gy >= 0 && gy < h;
 
   float phi, ksi;
-  one_px_outer<N>(c, a.sweeps, du, dv, phi, ksi);
+  one_px_outer<N>(c, a.sweeps, a.exact != 0, du, dv, phi, ksi);
   if (gx >= ox0 && gx < ox1 && gy >= oy0 && gy < oy1) {
     const size_t o = (size_t)gy * a.pitch + gx;
     a.du_out[o] = du;

@@ -12,7 +12,7 @@
 //       <out>NNNN_flow-u-W-H.raw / NNNN_flow-v-W-H.raw (and NNNN_res.pgm / NNNN_amp-W-H.raw on request)
 //   any pair form + trailing --residuals                                                                   (new)
 //       prints the RMS residual of every level's last linear system (flow2d_level_residuals)
-// Differences: no getchar() at exit; the 8-bit reader is wired to Mode@imageType="8-bit";
+// Differences: no getchar() at exit; 8-bit and float32 input files are told apart by their size (Mode@imageType only breaks ties);
 // files are also looked up under Input/Path@inputPath when they are not found in the CWD.
 #include <cmath>
 #include <cstdio>
@@ -107,6 +107,15 @@ static bool exists(const string& p) {
   return f != nullptr;
 }
 
+static long long file_size(const string& p) {  // -1 if the file cannot be opened
+  std::FILE* f = std::fopen(p.c_str(), "rb");
+  if (!f) return -1;
+  long long n = -1;
+  if (std::fseek(f, 0, SEEK_END) == 0) n = std::ftell(f);
+  std::fclose(f);
+  return n;
+}
+
 int main(int argc, char** argv) {
   std::printf("//----------------------------------------------------------------------//\n");
   std::printf("//   2D optical flow, Blackwell-native (%s)   //\n", flow2d_version());
@@ -188,12 +197,17 @@ int main(int argc, char** argv) {
   DataSize3 data_size = {width, height, 1};
   if (!optical_flow.Initialize(data_size, data_constancy)) return 1;
 
+  // The reference always calls ReadRAWFromFileF32 and ignores Mode@imageType (src/main.cpp:175-183); its stock
+  // settings.xml nevertheless says imageType="8-bit".  So the reader follows the FILE: W*H bytes = 8-bit, 4*W*H bytes =
+  // float32 (the same rule as the sequence driver); imageType only breaks the tie of a size that is neither.
   Data2D frame_0, frame_1;
-  const bool loaded = eight_bit ? (frame_0.ReadRAWFromFileU8(file_name1.c_str(), width, height) &&
-                                   frame_1.ReadRAWFromFileU8(file_name2.c_str(), width, height))
-                                : (frame_0.ReadRAWFromFileF32(file_name1.c_str(), width, height) &&
-                                   frame_1.ReadRAWFromFileF32(file_name2.c_str(), width, height));
-  if (!loaded) return 2;
+  auto read_frame = [&](Data2D& d, const string& name) {
+    const long long bytes = file_size(name);
+    const long long px = (long long)width * (long long)height;
+    const bool u8 = bytes == px ? true : bytes == 4 * px ? false : eight_bit;
+    return u8 ? d.ReadRAWFromFileU8(name.c_str(), width, height) : d.ReadRAWFromFileF32(name.c_str(), width, height);
+  };
+  if (!read_frame(frame_0, file_name1) || !read_frame(frame_1, file_name2)) return 2;
 
   Data2D flow_u(width, height), flow_v(width, height);
   optical_flow.silent = true;
@@ -210,13 +224,25 @@ int main(int argc, char** argv) {
   params.PushValuePtr("gaussian_sigma", &gaussian_sigma);
   if (report_residuals) params.PushValuePtr("report_residuals", &report_residuals);
 
+  flow_u.ZeroData();
+  flow_v.ZeroData();
   optical_flow.ComputeFlow(frame_0, frame_1, flow_u, flow_v, params);
+  if (optical_flow.last_status() != 0) {
+    // upstream's ComputeFlow is void and main() writes whatever the buffers hold; a failed solve must not
+    // leave plausible-looking files behind
+    std::cerr << "TERMINATING. Optical flow computation failed (status " << optical_flow.last_status() << ")." << std::endl;
+    return 4;
+  }
 
   const string suffix = "-" + std::to_string(width) + "-" + std::to_string(height) + ".raw";
-  flow_u.WriteRAWToFileF32((output_path + counter + "flow-u" + suffix).c_str());
-  flow_v.WriteRAWToFileF32((output_path + counter + "flow-v" + suffix).c_str());
+  bool written = flow_u.WriteRAWToFileF32((output_path + counter + "flow-u" + suffix).c_str());
+  written = flow_v.WriteRAWToFileF32((output_path + counter + "flow-v" + suffix).c_str()) && written;
   IOUtils::WriteFlowToImageRGB(flow_u, flow_v, 10, output_path + counter + "res.pgm");  // src/main.cpp:212
   IOUtils::WriteMagnitudeToFileF32(flow_u, flow_v, output_path + counter + "amp" + suffix);
   optical_flow.Destroy();
+  if (!written) {
+    std::cerr << "TERMINATING. Cannot write the flow files to " << output_path << std::endl;
+    return 5;
+  }
   return 0;
 }

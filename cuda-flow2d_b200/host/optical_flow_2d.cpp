@@ -48,6 +48,7 @@ bool get(const OperationParameters& params, const char* owner, const char* key, 
 
 void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u, Data2D& flow_v,
                                 OperationParameters& params) {
+  last_status_ = FLOW2D_ERR_INVALID_ARGUMENT;  // until the solve has succeeded
   if (!handle_) {
     std::printf("Error: '%s' was not initialized.\n", GetName());
     return;
@@ -73,6 +74,7 @@ void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u
     }
   std::printf("\nStarting optical flow computation...\n");
   const int rc = flow2d_compute(handle_, frame_0.DataPtr(), frame_1.DataPtr(), flow_u.DataPtr(), flow_v.DataPtr(), &p);
+  last_status_ = rc;
   if (rc != FLOW2D_OK) {
     std::fprintf(stderr, "Error: '%s': %s (%d)\n", GetName(), flow2d_last_error(handle_), rc);
     return;

@@ -29,8 +29,12 @@ class OpticalFlow2D {
   bool silent = false;
   int device = 0;              // CUDA device of the handle (the reference always uses device 0)
   float last_gpu_time_ms = 0;  // what upstream prints as "Total GPU computation time"
+  // 0 after a successful ComputeFlow, else the flow2d_status of the failure (upstream's ComputeFlow is void and
+  // swallows every error: cuda_utils.h:33-51); lets a caller skip its writers instead of saving garbage
+  int last_status() const { return last_status_; }
 
  private:
   flow2d_handle* handle_ = nullptr;
   DataSize3 size_{0, 0, 0};
+  int last_status_ = 0;
 };

@@ -130,6 +130,11 @@ enum {
 FLOW2D_API int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts /* [FLOW2D_KERNEL_KINDS] */);
 FLOW2D_API const char* flow2d_kernel_kind_name(int kind);
 
+/* The level schedule of one (containers, parameters) combination is captured into a CUDA graph on first use and replayed
+ * afterwards; a handle keeps the 8 most recently used graphs, so a caller that rotates a few containers (a frame ring)
+ * never re-captures.  captures / replays count both since flow2d_create.  No reference counterpart. */
+FLOW2D_API int flow2d_graph_stats(const flow2d_handle* h, long long* captures, long long* replays);
+
 /* ---- opt-in convergence diagnostics -----------------------------------------
  * The reference runs fixed iteration counts and computes no norm (cuda_operation_solve_2d.cpp:229-299).
  * With flow2d_params.report_residuals = 1 every level additionally records the RMS residual of the

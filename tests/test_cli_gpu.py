@@ -177,3 +177,42 @@ def test_pair_form_with_residuals_flag(rub, tmp_path):
     assert all(np.isfinite(v) and v >= 0 for v in vals)
     for name in ("x_flow-u-584-388.raw", "x_flow-v-584-388.raw", "x_amp-584-388.raw", "x_res.pgm"):
         assert (tmp_path / "a" / name).read_bytes() == (tmp_path / "b" / name).read_bytes(), name
+
+
+def test_settings_form_float32_frames_with_stock_image_type(rub, tmp_path):
+    """The reference ignores Mode@imageType and always reads float32 (src/main.cpp:175-176), while its stock settings.xml
+    says imageType="8-bit": float32 frames with an unchanged template must load (the reader follows the file size)."""
+    f0, f1 = rub
+    f0.tofile(tmp_path / "a.raw")
+    f1.tofile(tmp_path / "b.raw")
+    (tmp_path / "out").mkdir()
+    xml = """<OpticalFlow>
+  <Input><Path inputPath="./"/><Mode Nx="584" Ny="388" imageType="8-bit"><Files file1="a.raw" file2="b.raw"/></Mode></Input>
+  <Parameters><Method mode="2d" run="flow" key="0"/>
+    <Solver><Iterations inner="5" outer="20"/><Warping levels="20" scaling="0.9" medianRadius="5"/>
+      <Model sigma="0.45" alpha="3.5" e_smooth="0.001" e_data="0.001"/></Solver></Parameters>
+  <Output><Path outputPath="out/"/></Output></OpticalFlow>"""
+    (tmp_path / "settings.xml").write_text(xml)
+    r = _run(CLI, [], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    u = np.fromfile(tmp_path / "out" / "flow-u-584-388.raw", np.float32).reshape(388, 584)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rub_c1a_reference.npz"))
+    assert np.all(u == z["u"])
+
+
+def test_failed_solve_is_not_reported_as_success(rub, tmp_path):
+    """A parameter the solver refuses (median size 9): non-zero exit code and no output files (upstream writes stale memory)."""
+    f0, f1 = rub
+    f0.tofile(tmp_path / "a.raw")
+    f1.tofile(tmp_path / "b.raw")
+    (tmp_path / "out").mkdir()
+    xml = """<OpticalFlow>
+  <Input><Path inputPath="./"/><Mode Nx="584" Ny="388" imageType="32-bit"><Files file1="a.raw" file2="b.raw"/></Mode></Input>
+  <Parameters><Method mode="2d" run="flow" key="0"/>
+    <Solver><Iterations inner="5" outer="2"/><Warping levels="3" scaling="0.9" medianRadius="9"/>
+      <Model sigma="0.45" alpha="3.5" e_smooth="0.001" e_data="0.001"/></Solver></Parameters>
+  <Output><Path outputPath="out/"/></Output></OpticalFlow>"""
+    (tmp_path / "settings.xml").write_text(xml)
+    r = _run(CLI, [], tmp_path)
+    assert r.returncode not in (0, 1, 2, 3), r.stdout.decode()[-2000:]
+    assert not (tmp_path / "out" / "flow-u-584-388.raw").exists()

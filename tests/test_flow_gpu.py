@@ -123,3 +123,58 @@ def test_launch_counts_by_kernel(pkg, synth, torch_):
     assert any(k.startswith("solve") for k in counts)
     fl.compute(f0, f1, p)
     assert fl.launch_counts() == counts
+
+
+def test_graph_cache_keeps_alternating_buffers(pkg, synth, torch_):
+    """A handle that alternates between a few (frames, flow) container sets -- bench.py's C4 batch, a frame ring -- must
+    replay its captured graphs: captures == number of distinct sets, never a re-capture (flow2d_graph_stats)."""
+    w, h = 160, 120
+    p = pkg.default_params(levels=8, outer=3)
+    fl = pkg.Flow2D(w, h)
+    sets, expect = [], []
+    for i in range(3):
+        f0, f1, _, _ = synth.make_pair(w, h, 20 + i)
+        expect.append(fl.compute(f0, f1, p))
+        sets.append((fl.to_container(f0, 0.0), fl.to_container(f1, 0.0), fl.container(0.0), fl.container(0.0)))
+    c0, _ = fl.graph_stats()
+    for it in range(32):
+        d0, d1, du, dv = sets[it % 3]
+        fl.compute_device(d0, d1, du, dv, p)
+    torch_.cuda.synchronize()
+    c1, replays = fl.graph_stats()
+    assert c1 - c0 == 3, (c0, c1)
+    assert replays >= 29
+    for (d0, d1, du, dv), (eu, ev) in zip(sets, expect):
+        assert np.array_equal(fl.from_container(du, w, h), eu) and np.array_equal(fl.from_container(dv, w, h), ev)
+
+
+def test_misaligned_containers_are_refused(pkg, synth, torch_):
+    """Stage entry points take float4 paths: a pointer that is only 4-byte aligned is an INVALID_ARGUMENT, not a device fault."""
+    w, h = 64, 48
+    fl = pkg.Flow2D(w, h)
+    big = torch_.zeros(h * fl.pitch + 8, dtype=torch_.float32, device="cuda")
+    off = big[1:1 + h * fl.pitch].view(h, fl.pitch)  # 4-byte aligned only
+    ok = [fl.container(0.0) for _ in range(5)]
+    with pytest.raises(pkg.Flow2DError):
+        fl.stage_warp(ok[0], ok[1], off, ok[2], ok[3], w, h, 1.0, 1.0)
+    with pytest.raises(pkg.Flow2DError):
+        fl.stage_blur(off, ok[0], w, h, 1.0)
+    with pytest.raises(pkg.Flow2DError):
+        fl.stage_median(ok[0], off, w, h, 5)
+    with pytest.raises(pkg.Flow2DError):
+        fl.stage_resample(off, w, h, ok[0], 32, 24)
+    fl.stage_warp(ok[0], ok[1], ok[2], ok[3], ok[4], w, h, 1.0, 1.0)  # the handle still works
+    torch_.cuda.synchronize()
+
+
+@pytest.mark.parametrize("es,ed", [(0.0, 0.001), (0.001, 0.0)])
+def test_zero_epsilon_is_exact(pkg, oracle, synth, torch_, es, ed):
+    """equation_smoothness = 0 or equation_data = 0 are legal: the one-pixel kernels take their plain IEEE variant."""
+    w, h = 96, 80
+    f0, f1, _, _ = synth.make_pair(w, h, 31, U0=(0.4, -0.2), U1=0.6, L=48.0)
+    cfg = dict(levels=6, outer=4, inner=5, alpha=10.0, sigma=0.8, median=3, e_smooth=es, e_data=ed)
+    fl = pkg.Flow2D(w, h)
+    u, v = fl.compute(f0, f1, pkg.default_params(**cfg))
+    ou, ov = oracle.compute_flow(f0, f1, oracle.make_params(**cfg))
+    same = (u == ou) | (np.isnan(u) & np.isnan(ou))
+    assert same.all() and ((v == ov) | (np.isnan(v) & np.isnan(ov))).all()
