@@ -360,7 +360,9 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
         }
       }
       if (!small) {
-        launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
+        static const bool v1 = std::getenv("FLOW2D_SOLVE_V1") != nullptr;  // A/B switch: the first-generation tiled kernel
+        if (v1) launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
+        else launch_solve_pass2(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
         TRY(check_launch(h, FLOW2D_K_SOLVE_PASS, 1));
       }
       cur_du = a.du_out; cur_dv = a.dv_out;
@@ -688,7 +690,7 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
   }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
-      solve_pass_configure() != cudaSuccess || cudaMemsetAsync(h->pool, 0, csize * ncont * sizeof(float), h->own_stream) != cudaSuccess ||
+      solve_pass_configure() != cudaSuccess || solve_pass2_configure() != cudaSuccess || cudaMemsetAsync(h->pool, 0, csize * ncont * sizeof(float), h->own_stream) != cudaSuccess ||
       cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
     (void)cudaGetLastError();
     flow2d_destroy(h);

@@ -59,6 +59,11 @@ cudaError_t solve_pass_configure();
 // rows > 0: launch only that many region rows (resident mode of a level with few rows)
 void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y, int rows = 0);
 
+// second generation of the tiled pass (solve_pass2.cu): eight pixels per thread, packed fp32; a.outer must be 1
+size_t solve_pass2_smem_bytes();
+cudaError_t solve_pass2_configure();
+void launch_solve_pass2(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y);
+
 // one pass of a mid-size level with one thread per pixel: ts x ts regions (ts = 32, 24 or 16), a.halo_x = a.halo_y =
 // a.sweeps + 1, a.ow = a.oh = ts - 2 * halo; phi/ksi are always computed in the pass (a.phi_in must be null)
 constexpr int kSmallTS = 32;
