@@ -324,13 +324,14 @@ def measure(ctx, key, steps, warmup, streams=0, pairs=0, detail=True, sample_clo
 
     transport = None
     if slab_mode and world > 1:
-        transport = slab_mod.NcclExchange(dist, rank, world, "cuda:%d" % dev, streams_[0])
-        the_slab = transport.slab()
+        # mailboxes wired through CUDA IPC handles; the halo rows then travel as peer stores + flags (csrc/slab.cu)
+        slab_mod.connect_ipc(fl, dist, rank, world, "cuda:%d" % dev)
+        transport = True
+    own0, own1 = fl.slab_rows() if slab_mode else (0, h)
 
     def step_device():
         if transport is not None:
-            with torch.cuda.stream(streams_[0]):
-                fl.compute_slab_device(din[0][0], din[0][1], dout[0][0], dout[0][1], params, the_slab)
+            fl.compute_slab_device(din[0][0], din[0][1], dout[0][0], dout[0][1], params)
             return
         for i in range(P):
             k = i % K
@@ -366,13 +367,14 @@ def measure(ctx, key, steps, warmup, streams=0, pairs=0, detail=True, sample_clo
 
     def step_e2e():
         if transport is not None:
-            # public API of the slab path works on device containers: the copies are the caller's
+            # public API of the slab path works on device containers: the copies are the caller's.  Every rank uploads
+            # both frames (the warp reads rows it cannot know in advance) and downloads its own rows of the flow.
             with torch.cuda.stream(streams_[0]):
                 din[0][0][:h, :w].copy_(hin[0][0], non_blocking=True)
                 din[0][1][:h, :w].copy_(hin[0][1], non_blocking=True)
-                fl.compute_slab_device(din[0][0], din[0][1], dout[0][0], dout[0][1], params, the_slab)
-                hout[0][0].copy_(dout[0][0][:h, :w], non_blocking=True)
-                hout[0][1].copy_(dout[0][1][:h, :w], non_blocking=True)
+                fl.compute_slab_device(din[0][0], din[0][1], dout[0][0], dout[0][1], params)
+                hout[0][0][own0:own1].copy_(dout[0][0][own0:own1, :w], non_blocking=True)
+                hout[0][1][own0:own1].copy_(dout[0][1][own0:own1, :w], non_blocking=True)
             return
         for i in range(P):
             handles[i % K].compute_async(hin[i][0], hin[i][1], params, hout[i][0], hout[i][1])
@@ -406,17 +408,19 @@ def measure(ctx, key, steps, warmup, streams=0, pairs=0, detail=True, sample_clo
         dev_ms, e2e_ms, t_wall, e2e_wall = tt.tolist()
 
     pix = w * h * steps * P * (1 if slab_mode else world)
+    slab_stats, n_slab_calls = (fl.slab_stats(), max(1, 2 * (steps + warmup))) if transport is not None else (None, 1)
     res = {
         "value": pix / (dev_ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": dev_ms / steps, "scaling": "strong" if slab_mode else "weak",
         "config": config_of(wl),
         "schedule": {"pairs_per_step_per_gpu": P, "concurrent_streams_per_gpu": K,
-                     "sharding": ("rows of the large levels slabbed across the GPUs; exchanges/step: %s, MB/step/rank: %s" %
-                                  ({k: v // max(1, steps * 2 + warmup * 2) for k, v in transport.calls.items()},
-                                   {k: round(v / 1e6 / max(1, steps * 2 + warmup * 2), 1) for k, v in transport.bytes.items()}))
+                     "sharding": ("rows of the %d largest levels slabbed across the GPUs, every stage on the rank's own rows; only "
+                                  "halo rows move (peer stores + flags over NVLink, no collective): %d exchanges and %.1f MB sent "
+                                  "per flow by rank 0" % (slab_stats["levels_slabbed"], slab_stats["exchanges"] // n_slab_calls,
+                                                          slab_stats["bytes_sent"] / 1e6 / n_slab_calls))
                      if transport is not None else "pair i -> GPU i mod N, one handle per pair in flight, no data-path collective"},
         "e2e": {"value": pix / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": 2 * w * h * 4 * P,
-                "d2h_bytes_per_step": 2 * w * h * 4 * P, "ms_per_step": e2e_ms / steps,
+                "d2h_bytes_per_step": 2 * w * (own1 - own0) * 4 * P, "ms_per_step": e2e_ms / steps,
                 "wall_ms_per_step": e2e_wall / steps * 1e3, "api": "flow2d_compute_async + flow2d_synchronize (pinned host in/out)",
                 "result_check": result_check},
         "gpu_launches": int(launches_per_step * steps),

@@ -95,8 +95,15 @@ def lib():
         L.flow2d_stage_median.argtypes = [vp, vp, vp, sz, sz, sz]
         L.flow2d_stage_add_median.argtypes = [vp, vp, vp, vp, sz, sz, sz]
         L.flow2d_debug_timing.argtypes = [vp, vp]
-        L.flow2d_compute_slab_device.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params), vp]
-        L.flow2d_stage_solve_slab.argtypes = [vp] * 7 + [sz, sz, C.c_float, C.c_float, C.POINTER(Params), vp]
+        L.flow2d_compute_slab_device.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params)]
+        L.flow2d_stage_solve_slab.argtypes = [vp] * 7 + [sz, sz, C.c_float, C.c_float, C.POINTER(Params), C.POINTER(C.c_int)]
+        L.flow2d_slab_mailbox.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+        L.flow2d_slab_export.argtypes = [vp, C.c_char_p]
+        L.flow2d_slab_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        L.flow2d_slab_connect.argtypes = [vp, C.c_int, C.c_int, vp, vp, sz]
+        L.flow2d_slab_rows.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
+        L.flow2d_slab_status.argtypes = [vp]
+        L.flow2d_slab_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
         _LIB = L
     return _LIB
 
@@ -246,14 +253,49 @@ class Flow2D:
     def compute_device(self, d_f0, d_f1, d_u, d_v, params):
         self._check(lib().flow2d_compute_device(self._h, _ptr(d_f0), _ptr(d_f1), _ptr(d_u), _ptr(d_v), C.byref(params)))
 
-    def compute_slab_device(self, d_f0, d_f1, d_u, d_v, params, slab):
-        """flow2d_compute_slab_device; `slab` is a cuda_flow2d_b200.slab.Slab (keep its transport object alive)."""
-        self._check(lib().flow2d_compute_slab_device(self._h, _ptr(d_f0), _ptr(d_f1), _ptr(d_u), _ptr(d_v), C.byref(params),
-                                                     C.cast(C.pointer(slab), C.c_void_p)))
+    # -- one large frame on several GPUs (row slabs; see cuda_flow2d_b200.slab for the wiring helpers) --
+    def slab_mailbox(self):
+        """(device address, bytes) of this handle's mailbox (flow2d_slab_mailbox)."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._check(lib().flow2d_slab_mailbox(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
 
-    def stage_solve_slab(self, d_f0, d_f1w, d_u, d_v, d_du, d_dv, w, h, hx, hy, params, slab):
+    def slab_export(self):
+        buf = C.create_string_buffer(64)
+        self._check(lib().flow2d_slab_export(self._h, buf))
+        return buf.raw
+
+    def slab_import(self, ipc_handle):
+        ptr = C.c_void_p()
+        self._check(lib().flow2d_slab_import(self._h, C.create_string_buffer(bytes(ipc_handle), 64), C.byref(ptr)))
+        return ptr.value
+
+    def slab_connect(self, rank, world, mailbox_above, mailbox_below, min_rows=0):
+        self._check(lib().flow2d_slab_connect(self._h, rank, world, C.c_void_p(mailbox_above or 0), C.c_void_p(mailbox_below or 0), min_rows))
+
+    def slab_rows(self, level_height=None):
+        a, b = C.c_size_t(), C.c_size_t()
+        self._check(lib().flow2d_slab_rows(self._h, level_height or self.height, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def slab_status(self):
+        """Waits for the handle's stream and raises if a wait for a neighbour timed out (flow2d_slab_status)."""
+        self._check(lib().flow2d_slab_status(self._h))
+
+    def slab_stats(self):
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_int()
+        self._check(lib().flow2d_slab_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"exchanges": a.value, "bytes_sent": b.value, "levels_slabbed": c.value}
+
+    def compute_slab_device(self, d_f0, d_f1, d_u, d_v, params):
+        """flow2d_compute_slab_device on a connected handle: this rank's rows (slab_rows()) of d_u, d_v are the result."""
+        self._check(lib().flow2d_compute_slab_device(self._h, _ptr(d_f0), _ptr(d_f1), _ptr(d_u), _ptr(d_v), C.byref(params)))
+
+    def stage_solve_slab(self, d_f0, d_f1w, d_u, d_v, d_du, d_dv, w, h, hx, hy, params):
+        slabbed = C.c_int()
         self._check(lib().flow2d_stage_solve_slab(self._h, _ptr(d_f0), _ptr(d_f1w), _ptr(d_u), _ptr(d_v), _ptr(d_du), _ptr(d_dv),
-                                                  w, h, hx, hy, C.byref(params), C.cast(C.pointer(slab), C.c_void_p)))
+                                                  w, h, hx, hy, C.byref(params), C.byref(slabbed)))
+        return bool(slabbed.value)
 
     def debug_timing(self, d_stamps):
         self._check(lib().flow2d_debug_timing(self._h, _ptr(d_stamps)))

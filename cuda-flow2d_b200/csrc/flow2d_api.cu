@@ -71,6 +71,17 @@ struct flow2d_handle {
   unsigned long long graph_clock = 0;
   long long graph_captures = 0, graph_replays = 0;
   int sm_count = 148;
+  // row-slab decomposition (flow2d_slab_connect): this handle is rank `slab_rank` of `slab_world`
+  int slab_rank = 0, slab_world = 1;
+  size_t slab_min_rows = 128;
+  unsigned char* mailbox = nullptr;          // own mailbox (its own cudaMalloc: CUDA IPC exports whole allocations)
+  size_t mailbox_bytes = 0, mailbox_rows = 0;
+  unsigned char* peer[2] = {nullptr, nullptr};  // mapped mailboxes of rank-1 (above) and rank+1 (below)
+  void* imported[2] = {nullptr, nullptr};    // cudaIpcOpenMemHandle mappings to close at destroy
+  unsigned long long slab_epoch = 0;         // exchanges so far (same sequence on every rank)
+  unsigned* slab_counter = nullptr;
+  long long slab_exchanges = 0, slab_bytes_sent = 0;
+  int slab_levels = 0;
   std::string err;
 };
 
@@ -178,12 +189,138 @@ LevelGeom geom(const flow2d_handle* h, size_t w, size_t hh, float hx, float hy) 
   return g;
 }
 
-// CudaOperationSolve2D::Execute (cuda_operation_solve_2d.cpp:229-299) on top of solve_pass.
+// ---- row-slab decomposition ---------------------------------------------------------------------------------------
+// Rank r owns rows [Y0, Y1) of a slabbed level.  Everything a level computes is computed on the own rows plus the
+// margins the next stage needs; only rows of neighbours ever move:
+//   solve      du, dv exact on [Y0 - ghost, Y1 + ghost) after an exchange; a pass loses S+1 rows at each cut edge, so the
+//              ghost rows are refreshed from the two neighbours every `outers_per_exchange` outer iterations
+//   inputs     u, v, fx, fy, ft on own +- (ghost + S + 1) rows (what the passes read), warped frame one row more
+//   median     u + du on own +- median/2 rows: the solve ends with that much validity to spare (no extra exchange)
+//   next level its prolongation reads own +- ~30 rows of this level's flow: one exchange of u, v rows after the median
+// Both frames (and their restrictions) are complete on every rank: the warp gathers rows it cannot know in advance.
+constexpr int kSlabHeaderBytes = 256;
+constexpr size_t kSlabRowsCap = 128;  // rows per message the mailbox can hold
+
+struct SolvePlan {
+  int S = 1, npass = 1;
+  bool slabbed = false;
+  int Y0 = 0, Y1 = 0;               // own rows
+  int ghost = 0;                    // rows of du/dv received from each neighbour per exchange
+  int outers_per_exchange = 4;
+  int keep = 0;                     // rows beyond the own rows on which the increment must still be exact at the end
+  int in_margin = 0;                // u, v, fx, fy, ft are needed on own +- in_margin rows
+};
+
+void slab_own_rows(int h, int rank, int world, int* y0, int* y1) {
+  const int base = h / world, extra = h % world;
+  *y0 = rank * base + (rank < extra ? rank : extra);
+  *y1 = *y0 + base + (rank < extra ? 1 : 0);
+}
+
+SolvePlan plan_solve(const flow2d_handle* h, const LevelGeom& g, const flow2d_params* p, int median, bool allow_slab) {
+  SolvePlan pl;
+  const int inner = (int)p->inner_iterations_count;
+  int S = p->sweeps_per_pass;
+  if (S <= 0) {
+    // Pick the sweeps per pass that minimises the modelled solve time.  Measured on B200 with solve_pass2
+    // (tools/phase_timing.py, profiles/r02): per wave of CTAs a pass costs ~4.9 us of setup and hand-over when it
+    // computes phi/ksi, ~3.7 us when it reloads them, plus ~0.65 us per sweep; region 64 x 48, halo S+1 rows and
+    // 4 (S <= 3) or 8 columns per side.
+    double best = 1e300;
+    for (int s_ = 1; s_ <= FLOW2D_MAX_SWEEPS_PER_PASS; ++s_) {
+      const int np = (inner + s_ - 1) / s_;
+      const int ow = kSolveLW - 2 * ((s_ + 1 <= 4) ? 4 : 8), oh = kSolveLH - 2 * (s_ + 1);
+      double waves = (double)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) / (double)h->sm_count;
+      if (waves < 1.0) waves = 1.0;
+      const double cost = waves * (4.9 + (np - 1) * 3.7 + 0.65 * inner);
+      if (cost < best) { best = cost; S = s_; }
+    }
+  }
+  if (S > FLOW2D_MAX_SWEEPS_PER_PASS) S = FLOW2D_MAX_SWEEPS_PER_PASS;
+  if (S > inner && inner > 0) S = inner;
+  pl.S = S;
+  pl.npass = inner > 0 ? (inner + S - 1) / S : 1;
+  pl.Y0 = 0; pl.Y1 = g.h;
+  if (allow_slab && h->slab_world > 1 && inner > 0 && p->outer_iterations_count > 0) {
+    // rows lost per outer iteration: every pass s_q + 1 (the sweeps are spread evenly over the passes)
+    int per_outer = 0, left = inner;
+    for (int q = 0; q < pl.npass; ++q) {
+      const int s_ = (left + (pl.npass - q) - 1) / (pl.npass - q);
+      left -= s_;
+      per_outer += s_ + 1;
+    }
+    pl.keep = median / 2;
+    int k = 4;
+    while (k > 1 && (size_t)(per_outer * k + pl.keep) > kSlabRowsCap) --k;
+    pl.outers_per_exchange = k;
+    pl.ghost = per_outer * k + pl.keep;
+    const int base = g.h / h->slab_world;
+    // the next level's prolongation takes up to ~ (ghost + S + 3) rows of this level from the neighbours
+    if ((size_t)base >= h->slab_min_rows && base >= 2 * (pl.ghost + S + 4) && (size_t)pl.ghost <= kSlabRowsCap) {
+      pl.slabbed = true;
+      slab_own_rows(g.h, h->slab_rank, h->slab_world, &pl.Y0, &pl.Y1);
+      pl.in_margin = pl.ghost + S + 1;
+    }
+  }
+  return pl;
+}
+
+// One message to / from each neighbour: rows [up0, up0+upn) of (fa, fb) go to the rank above, [dn0, dn0+dnn) to the rank
+// below; rows [rup0, +rupn) arrive from above and [rdn0, +rdnn) from below (same row indices on both sides).
+int slab_exchange(flow2d_handle* h, float* fa, float* fb, const LevelGeom& g, int up0, int upn, int dn0, int dnn, int rup0,
+                  int rupn, int rdn0, int rdnn) {
+  if (h->slab_rank == 0) upn = rupn = 0;
+  if (h->slab_rank == h->slab_world - 1) dnn = rdnn = 0;
+  if ((size_t)upn > h->mailbox_rows || (size_t)dnn > h->mailbox_rows || (size_t)rupn > h->mailbox_rows || (size_t)rdnn > h->mailbox_rows)
+    return fail(h, FLOW2D_ERR_UNSUPPORTED, "slab exchange of %d rows exceeds the mailbox (%zu rows)", upn > dnn ? upn : dnn, h->mailbox_rows);
+  if ((upn > 0 && !h->peer[0]) || (dnn > 0 && !h->peer[1])) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "slab: neighbour mailbox not connected");
+  const unsigned long long e = ++h->slab_epoch;
+  const size_t plane = h->mailbox_rows * h->pitch;  // floats per receive buffer
+  auto recv_buf = [&](unsigned char* box, int from, int field) {
+    return reinterpret_cast<float*>(box + kSlabHeaderBytes) + ((size_t)((from * 2 + (int)(e & 1)) * 2 + field)) * plane;
+  };
+  auto flag_of = [&](unsigned char* box, int from) { return reinterpret_cast<unsigned long long*>(box) + from; };
+  SlabPush ps;
+  std::memset(&ps, 0, sizeof ps);
+  ps.field[0] = fa; ps.field[1] = fb;
+  ps.counter = h->slab_counter;
+  ps.w = g.w; ps.pitch = g.pitch;
+  if (upn > 0) {  // to the rank above: it receives "from below" (index 1)
+    ps.dir[0].dst[0] = recv_buf(h->peer[0], 1, 0); ps.dir[0].dst[1] = recv_buf(h->peer[0], 1, 1);
+    ps.dir[0].flag = flag_of(h->peer[0], 1); ps.dir[0].epoch = e; ps.dir[0].row0 = up0; ps.dir[0].rows = upn;
+  }
+  if (dnn > 0) {  // to the rank below: it receives "from above" (index 0)
+    ps.dir[1].dst[0] = recv_buf(h->peer[1], 0, 0); ps.dir[1].dst[1] = recv_buf(h->peer[1], 0, 1);
+    ps.dir[1].flag = flag_of(h->peer[1], 0); ps.dir[1].epoch = e; ps.dir[1].row0 = dn0; ps.dir[1].rows = dnn;
+  }
+  launch_slab_push(h->stream, ps);
+  SlabUnpack up;
+  std::memset(&up, 0, sizeof up);
+  up.field[0] = fa; up.field[1] = fb;
+  up.error = h->slab_counter + 1;
+  up.w = g.w; up.pitch = g.pitch;
+  if (rupn > 0) {
+    up.dir[0].src[0] = recv_buf(h->mailbox, 0, 0); up.dir[0].src[1] = recv_buf(h->mailbox, 0, 1);
+    up.dir[0].flag = flag_of(h->mailbox, 0); up.dir[0].epoch = e; up.dir[0].row0 = rup0; up.dir[0].rows = rupn;
+  }
+  if (rdnn > 0) {
+    up.dir[1].src[0] = recv_buf(h->mailbox, 1, 0); up.dir[1].src[1] = recv_buf(h->mailbox, 1, 1);
+    up.dir[1].flag = flag_of(h->mailbox, 1); up.dir[1].epoch = e; up.dir[1].row0 = rdn0; up.dir[1].rows = rdnn;
+  }
+  launch_slab_unpack(h->stream, up);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(h, FLOW2D_ERR_CUDA, "slab exchange launch failed: %s", cudaGetErrorString(err));
+  ++h->slab_exchanges;
+  h->slab_bytes_sent += (long long)(upn + dnn) * g.w * 2 * 4;
+  return FLOW2D_OK;
+}
+
+// CudaOperationSolve2D::Execute (cuda_operation_solve_2d.cpp:229-299) on top of the solve kernels.
 // The result is left in du_a/dv_a; du_b/dv_b are scratch.  fx,fy,ft (and J in gradient mode) must
-// hold the derivative planes of this level.
+// hold the derivative planes of this level (on the own rows +- plan.in_margin when the level is slabbed).
 int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float* v, float* du_a, float* dv_a,
               float* du_b, float* dv_b, float* phi, float* ksi, bool want_phi, const flow2d_params* p,
-              const flow2d_slab* slab = nullptr) {
+              const SolvePlan& pl) {
   const int outer = (int)p->outer_iterations_count, inner = (int)p->inner_iterations_count;
   if (outer == 0 || inner == 0) {
     // no sweep runs: the increment stays at its initial zero (cuda_operation_solve_2d.cpp:229-232)
@@ -208,9 +345,10 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   // the branch-free sqrt / rcp of the one-pixel kernels cover: take their plain IEEE variant from the start instead of
   // computing every outer iteration twice
   a.exact = (a.e_smooth * a.e_smooth < 0x1p-100f || a.e_data * a.e_data < 0x1p-100f) ? 1 : 0;
+  const bool slabbed = pl.slabbed;
 
   // tiny levels (<= 1024 pixels): one CTA, one thread per pixel, all outer iterations in the kernel
-  if (p->resident_levels >= 0 && p->resident_levels != 2 && solve_tiny_fits(g.w, g.h)) {
+  if (!slabbed && p->resident_levels >= 0 && p->resident_levels != 2 && solve_tiny_fits(g.w, g.h)) {
     a.du_in = a.dv_in = nullptr;
     a.phi_in = a.ksi_in = nullptr;
     a.du_out = du_a; a.dv_out = dv_a;
@@ -228,7 +366,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   const bool small_pass_instead = p->resident_levels == 0 && !p->throughput_mode && outer > 1 &&
                                   (p->sweeps_per_pass == 0 || p->sweeps_per_pass >= inner) &&
                                   inner <= FLOW2D_MAX_SWEEPS_PER_PASS && kSmallTS - 2 * (inner + 1) >= 4;
-  if (fits && p->resident_levels >= 0 && !small_pass_instead) {
+  if (!slabbed && fits && p->resident_levels >= 0 && !small_pass_instead) {
     a.du_in = a.dv_in = nullptr;
     a.phi_in = a.ksi_in = nullptr;
     a.du_out = du_a; a.dv_out = dv_a;
@@ -239,24 +377,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
     return check_launch(h, FLOW2D_K_SOLVE_RESIDENT, 1);
   }
 
-  int S = p->sweeps_per_pass;
-  if (S <= 0) {
-    // Pick the sweeps per pass that minimises the modelled solve time.  Measured on B200 (ncu and
-    // bench.py, profiles/): per wave of CTAs a pass costs ~11 us of setup when it computes phi/ksi,
-    // ~7.5 us when it reloads them, plus ~0.85 us per sweep; region 64 x 48, halo S+1 rows and
-    // 4 (S <= 3) or 8 columns per side.
-    double best = 1e300;
-    for (int s = 1; s <= FLOW2D_MAX_SWEEPS_PER_PASS; ++s) {
-      const int np = (inner + s - 1) / s;
-      const int ow = kSolveLW - 2 * ((s + 1 <= 4) ? 4 : 8), oh = kSolveLH - 2 * (s + 1);
-      double waves = (double)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) / (double)h->sm_count;
-      if (waves < 1.0) waves = 1.0;
-      const double cost = waves * (11.0 + (np - 1) * 7.5 + 0.85 * inner);
-      if (cost < best) { best = cost; S = s; }
-    }
-  }
-  if (S > FLOW2D_MAX_SWEEPS_PER_PASS) S = FLOW2D_MAX_SWEEPS_PER_PASS;
-  const int npass = (inner + S - 1) / S;
+  const int S = pl.S, npass = pl.npass;
   const long long total = (long long)outer * npass;
   float* bufs[2][2] = {{du_a, dv_a}, {du_b, dv_b}};
   long long pass = 0;
@@ -264,25 +385,13 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   float *cur_du = nullptr, *cur_dv = nullptr;
   a.outer = 1;
 
-  // Row-slab decomposition (flow2d.h): this rank produces rows [Y0, Y1) of the level.  A pass can
-  // only be exact where its input increment was exact S+1 rows further out, so the rows a rank
-  // works on shrink by S+1 per pass from both cut edges (never at the true image border) until the
-  // ghost rows are refreshed from the neighbours.  Exchanges happen between outer iterations only
-  // (phi / ksi of a multi-pass outer iteration are not exchanged).
-  int Y0 = 0, Y1 = g.h, ghost = 0;
-  bool slabbed = false;
-  if (slab && slab->world > 1) {
-    const int per_outer = npass * (S + 1);                   // rows lost per outer iteration
-    const int outers_per_exchange = 4;
-    ghost = per_outer * outers_per_exchange;
-    const size_t min_rows = slab->min_rows_per_rank ? slab->min_rows_per_rank : 128;
-    const int base = g.h / slab->world, extra = g.h % slab->world;
-    if ((size_t)base >= min_rows && base >= 2 * ghost) {
-      slabbed = true;
-      Y0 = slab->rank * base + (slab->rank < extra ? slab->rank : extra);
-      Y1 = Y0 + base + (slab->rank < extra ? 1 : 0);
-    }
-  }
+  // Row-slab decomposition: this rank produces rows [Y0, Y1) of the level (+- keep).  A pass can only be exact where
+  // its input increment was exact S+1 rows further out, so the rows a rank works on shrink by S+1 per pass from both
+  // cut edges (never at the true image border) until the ghost rows are refreshed from the neighbours.  Exchanges
+  // happen between outer iterations only (phi / ksi of a multi-pass outer iteration are not exchanged).
+  const int Y0 = pl.Y0, Y1 = pl.Y1, ghost = pl.ghost;
+  // rows that must stay exact to the end: the own rows and what the median reads beyond them
+  const int K0 = slabbed ? (Y0 - pl.keep > 0 ? Y0 - pl.keep : 0) : 0, K1 = slabbed ? (Y1 + pl.keep < g.h ? Y1 + pl.keep : g.h) : g.h;
   int va = 0, vb = g.h;  // rows on which the current increment is exact on this rank
   if (slabbed) {
     va = Y0 - ghost > 0 ? Y0 - ghost : 0;
@@ -291,7 +400,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   bool after_exchange = false;
   for (int o = 0; o < outer; ++o) {
     if (slabbed && o > 0) {
-      // would this outer iteration still cover the rank's own rows?
+      // would this outer iteration still cover the rows that have to stay exact?
       int sa = va, sb = vb, left = inner;
       for (int q = 0; q < npass; ++q) {
         const int s = (left + (npass - q) - 1) / (npass - q);
@@ -299,10 +408,9 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
         if (sa > 0) sa += s + 1;
         if (sb < g.h) sb -= s + 1;
       }
-      if (sa > Y0 || sb < Y1) {
-        if (slab->exchange(slab->user, 0, cur_du, cur_dv, h->pitch, (size_t)g.w, (size_t)g.h, (size_t)Y0, (size_t)Y1,
-                           (size_t)ghost) != 0)
-          return fail(h, FLOW2D_ERR_CUDA, "slab halo exchange failed");
+      if (sa > K0 || sb < K1) {
+        // ghost rows of the increment: [Y0, Y0+ghost) to the rank above, [Y1-ghost, Y1) to the rank below
+        TRY(slab_exchange(h, cur_du, cur_dv, g, Y0, ghost, Y1 - ghost, ghost, Y0 - ghost, ghost, Y1, ghost));
         va = Y0 - ghost > 0 ? Y0 - ghost : 0;
         vb = Y1 + ghost < g.h ? Y1 + ghost : g.h;
         after_exchange = true;
@@ -334,13 +442,13 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       // Mid-size levels cannot fill the GPU with 64x48 regions; there the latency of one CTA is what
       // counts and the one-thread-per-pixel pass is faster as long as its many more CTAs still fit a few
       // waves.  Time model fitted to tools/level_timing.py on B200 (us per outer iteration, launch gap included):
-      //   tiled 64x48 tiles   0.7 + 11.1 * max(1, tiles / 148)
+      //   tiled 64x48 tiles   0.7 + (4.9 + 0.65 * sweeps) * max(1, tiles / 148)   (solve_pass2; 11.1 per wave with the first generation)
       //   ts x ts regions     1.0 + ceil(regions / 148) * (2.5 + 1.6 * ts^2 / 1024)
       bool small = false;
       if (npass == 1 && p->resident_levels != 2 && p->resident_levels != -1 && !p->throughput_mode) {
         const long long n_big = (long long)((g.w + a.ow - 1) / a.ow) * ((vb - va + a.oh - 1) / a.oh);
         const long long sms = h->sm_count;
-        double t_best = 0.7 + 11.1 * (n_big > sms ? (double)n_big / (double)sms : 1.0);
+        double t_best = 0.7 + (4.9 + 0.65 * s) * (n_big > sms ? (double)n_big / (double)sms : 1.0);
         int ts_best = 0;
         static const int kRegion[3] = {32, 24, 16};
         for (int ts : kRegion) {
@@ -368,19 +476,21 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       cur_du = a.du_out; cur_dv = a.dv_out;
     }
   }
-  if (slabbed) {
-    if (slab->exchange(slab->user, 1, du_a, dv_a, h->pitch, (size_t)g.w, (size_t)g.h, (size_t)Y0, (size_t)Y1, 0) != 0)
-      return fail(h, FLOW2D_ERR_CUDA, "slab gather failed");
-  }
   return FLOW2D_OK;
 }
 
-int run_derivatives(flow2d_handle* h, const LevelGeom& g, const float* f0, const float* f1w) {
-  launch_derivatives(h->stream, f0, f1w, h->c[C_FX], h->c[C_FY], h->c[C_FT], g);
+// y0, y1: rows on which the solve needs fx, fy, ft (y1 <= y0: the whole level).  Gradient constancy takes central
+// differences of them (inside the reference's 16x8 tiles), so the derivative planes cover one row more on each side.
+int run_derivatives(flow2d_handle* h, const LevelGeom& g, const float* f0, const float* f1w, int y0 = 0, int y1 = 0) {
+  const bool grad = h->constancy == FLOW2D_GRADIENT;
+  if (y1 <= y0) { y0 = 0; y1 = g.h; }
+  const int e = grad ? 1 : 0;
+  const int d0 = y0 - e > 0 ? y0 - e : 0, d1 = y1 + e < g.h ? y1 + e : g.h;
+  launch_derivatives(h->stream, f0, f1w, h->c[C_FX], h->c[C_FY], h->c[C_FT], g, d0, d1);
   TRY(check_launch(h, FLOW2D_K_DERIVATIVES, 1));
-  if (h->constancy == FLOW2D_GRADIENT) {
+  if (grad) {
     float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
-    launch_grad_tensor(h->stream, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, g);
+    launch_grad_tensor(h->stream, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, g, y0, y1);
     TRY(check_launch(h, FLOW2D_K_GRAD_TENSOR, 1));
   }
   return FLOW2D_OK;
@@ -402,15 +512,19 @@ int validate_params(flow2d_handle* h, const flow2d_params* p, int* median) {
 }
 
 // The pyramid.  frame_0 / frame_1 / out_u / out_v are device containers.
+// With `slab` (flow2d_compute_slab_device on a connected handle) the large levels are slabbed by rows: this rank then
+// produces its own rows of every stage (plus the margins the next stage needs) and of the final flow.
 int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1, float* out_u, float* out_v,
-                    const flow2d_params* p, const flow2d_slab* slab = nullptr) {
+                    const flow2d_params* p, bool slab = false) {
   int median = 1;
   TRY(validate_params(h, p, &median));
   const size_t W = h->W, H = h->H;
   cudaStream_t st = h->stream;
   h->levels_run = 0;
-  const bool residuals = p->report_residuals != 0 && !(slab && slab->world > 1);
+  const bool slab_on = slab && h->slab_world > 1;
+  const bool residuals = p->report_residuals != 0 && !slab_on;
   h->residual_levels = 0;
+  h->slab_levels = 0;
   if (residuals) CU_TRY(h, cudaMemsetAsync(h->d_residuals, 0, sizeof(double) * 2 * FLOW2D_MAX_LEVELS, st));
 
   // presmoothing (optical_flow_2d.cpp:218-246)
@@ -429,12 +543,25 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
   int level = (int)(p->warp_levels_count < max_level ? p->warp_levels_count : max_level) - 1;
   float *u = h->c[C_U], *v = h->c[C_V], *u2 = h->c[C_U2], *v2 = h->c[C_V2];
   size_t pw = 0, ph = 0;
+  const int e = h->constancy == FLOW2D_GRADIENT ? 1 : 0;
+  bool prev_slabbed = false;
 
   while (level >= 0) {
     size_t cw, ch;
     float hx, hy;
     flow2d_level_geometry(W, H, p->warp_scale_factor, level, &cw, &ch, &hx, &hy);
     const LevelGeom g = geom(h, cw, ch, hx, hy);
+    const SolvePlan pl = plan_solve(h, g, p, median, slab_on);
+    if (prev_slabbed && !pl.slabbed) return fail(h, FLOW2D_ERR_UNSUPPORTED, "slab: level %dx%d cannot be slabbed after a slabbed coarser level", g.w, g.h);
+    // rows of this level on which the stages work: D = derivative planes, Wr = warped frame and flow
+    int D0 = 0, D1 = g.h, W0 = 0, W1 = g.h;
+    if (pl.slabbed) {
+      ++h->slab_levels;
+      D0 = pl.Y0 - pl.in_margin > 0 ? pl.Y0 - pl.in_margin : 0;
+      D1 = pl.Y1 + pl.in_margin < g.h ? pl.Y1 + pl.in_margin : g.h;
+      W0 = D0 - 1 - e > 0 ? D0 - 1 - e : 0;
+      W1 = D1 + 1 + e < g.h ? D1 + 1 + e : g.h;
+    }
 
     // frames of this level: always restricted from the full-resolution frames (279-305);
     // flow of this level: zero, or prolongated from the previous level (308-341).
@@ -444,16 +571,17 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     ResampleJob jobs[4];
     int njobs = 0;
     if (level != 0) {
-      jobs[njobs++] = ResampleJob{frame[0], h->c[C_TMP0], h->c[C_RES0], (int)W, (int)H, g.w, g.h};
-      jobs[njobs++] = ResampleJob{frame[1], h->c[C_TMP1], h->c[C_RES1], (int)W, (int)H, g.w, g.h};
+      // (frame 1 is needed wherever the flow may point: all rows; frame 0 on the rows that are warped / differentiated)
+      jobs[njobs++] = ResampleJob{frame[0], h->c[C_TMP0], h->c[C_RES0], (int)W, (int)H, g.w, g.h, W0, W1, 0, 0};
+      jobs[njobs++] = ResampleJob{frame[1], h->c[C_TMP1], h->c[C_RES1], (int)W, (int)H, g.w, g.h, 0, 0, 0, 0};
       fr[0] = h->c[C_RES0]; fr[1] = h->c[C_RES1];
     }
     if (pw == 0) {
       CU_TRY(h, cudaMemset2DAsync(u, h->pitch * 4, 0, cw * 4, ch, st));
       CU_TRY(h, cudaMemset2DAsync(v, h->pitch * 4, 0, cw * 4, ch, st));
     } else {
-      jobs[njobs++] = ResampleJob{u, h->c[C_DU1], u2, (int)pw, (int)ph, g.w, g.h};
-      jobs[njobs++] = ResampleJob{v, h->c[C_DV1], v2, (int)pw, (int)ph, g.w, g.h};
+      jobs[njobs++] = ResampleJob{u, h->c[C_DU1], u2, (int)pw, (int)ph, g.w, g.h, W0, W1, 0, 0};
+      jobs[njobs++] = ResampleJob{v, h->c[C_DV1], v2, (int)pw, (int)ph, g.w, g.h, W0, W1, 0, 0};
       std::swap(u, u2); std::swap(v, v2);
     }
     if (njobs) {
@@ -461,11 +589,11 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
       TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
     }
     // backward registration (344-363) and the level's derivative planes
-    launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g);
+    launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g, W0, W1);
     TRY(check_launch(h, FLOW2D_K_WARP, 1));
-    TRY(run_derivatives(h, g, fr[0], h->c[C_WARPED]));
+    TRY(run_derivatives(h, g, fr[0], h->c[C_WARPED], D0, D1));
     // solve (366-406)
-    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], residuals, p, slab));
+    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], residuals, p, pl));
     if (residuals && h->residual_levels < FLOW2D_MAX_LEVELS && p->outer_iterations_count > 0 && p->inner_iterations_count > 0) {
       const float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
       launch_residual(st, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, h->constancy == FLOW2D_GRADIENT, u, v, h->c[C_DU0],
@@ -474,14 +602,58 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
       h->residual_px[h->residual_levels++] = g.w * g.h;
     }
     // u += du, v += dv, median (409-449); the finest level writes the caller's flow containers
+    float* nu = level == 0 ? out_u : u2;
+    float* nv = level == 0 ? out_v : v2;
     {
       const float* a[2] = {u, v};
       const float* b[2] = {h->c[C_DU0], h->c[C_DV0]};
-      float* out[2] = {level == 0 ? out_u : u2, level == 0 ? out_v : v2};
-      launch_add_median(st, a, b, out, 2, g.w, g.h, g.pitch, median);
+      float* out[2] = {nu, nv};
+      launch_add_median(st, a, b, out, 2, g.w, g.h, g.pitch, median, pl.Y0, pl.Y1);
       TRY(check_launch(h, FLOW2D_K_ADD_MEDIAN, 1));
       std::swap(u, u2); std::swap(v, v2);
     }
+    // slabbed: the next level's prolongation reads rows of this level's flow that the neighbours own
+    if (pl.slabbed && level > 0) {
+      size_t nw, nh;
+      float nhx, nhy;
+      flow2d_level_geometry(W, H, p->warp_scale_factor, level - 1, &nw, &nh, &nhx, &nhy);
+      const LevelGeom ng = geom(h, nw, nh, nhx, nhy);
+      const SolvePlan npl = plan_solve(h, ng, p, median, true);
+      if (!npl.slabbed) return fail(h, FLOW2D_ERR_UNSUPPORTED, "slab: finer level %dx%d not slabbed", ng.w, ng.h);
+      // rows [lo_q, hi_q) of THIS level that rank q reads when it prolongates to its rows of the next level
+      auto needs = [&](int q, int* lo, int* hi) {
+        int z0, z1;
+        slab_own_rows(ng.h, q, h->slab_world, &z0, &z1);
+        const int m = npl.in_margin + 1 + e;
+        const int o0 = z0 - m > 0 ? z0 - m : 0, o1 = z1 + m < ng.h ? z1 + m : ng.h;
+        const float delta = (float)g.h / (float)ng.h;  // as in the resampler: rows of this level per row of the next
+        *lo = (int)floorf((float)o0 * delta);
+        const int t = (int)ceilf((float)o1 * delta);
+        *hi = t < g.h ? t : g.h;
+      };
+      const int r = h->slab_rank;
+      int lo, hi, up0 = 0, upn = 0, dn0 = 0, dnn = 0, rup0 = 0, rupn = 0, rdn0 = 0, rdnn = 0;
+      needs(r, &lo, &hi);
+      if (lo < pl.Y0) { rup0 = lo; rupn = pl.Y0 - lo; }
+      if (hi > pl.Y1) { rdn0 = pl.Y1; rdnn = hi - pl.Y1; }
+      if (r > 0) {  // what the rank above reads below its own rows = my first rows
+        int l2, h2, a0, a1;
+        needs(r - 1, &l2, &h2);
+        slab_own_rows(g.h, r - 1, h->slab_world, &a0, &a1);
+        if (h2 > a1) { up0 = a1; upn = h2 - a1; }
+        if (rupn > a1 - a0) return fail(h, FLOW2D_ERR_UNSUPPORTED, "slab: halo exceeds the neighbour's rows");
+      }
+      if (r < h->slab_world - 1) {
+        int l2, h2, b0, b1;
+        needs(r + 1, &l2, &h2);
+        slab_own_rows(g.h, r + 1, h->slab_world, &b0, &b1);
+        if (l2 < b0) { dn0 = l2; dnn = b0 - l2; }
+        if (rdnn > b1 - b0) return fail(h, FLOW2D_ERR_UNSUPPORTED, "slab: halo exceeds the neighbour's rows");
+      }
+      if (upn > pl.Y1 - pl.Y0 || dnn > pl.Y1 - pl.Y0) return fail(h, FLOW2D_ERR_UNSUPPORTED, "slab: halo exceeds the own rows");
+      TRY(slab_exchange(h, nu, nv, g, up0, upn, dn0, dnn, rup0, rupn, rdn0, rdnn));
+    }
+    prev_slabbed = pl.slabbed;
     pw = cw; ph = ch;
     --level;
     ++h->levels_run;
@@ -710,6 +882,10 @@ int flow2d_destroy(flow2d_handle* h) {
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (void* m : h->imported)
+    if (m) cudaIpcCloseMemHandle(m);
+  if (h->mailbox) cudaFree(h->mailbox);
+  if (h->slab_counter) cudaFree(h->slab_counter);
   if (h->pool) cudaFree(h->pool);
   if (h->d_residuals) cudaFree(h->d_residuals);
   delete h;
@@ -842,34 +1018,134 @@ int flow2d_compute(flow2d_handle* h, const float* frame_0, const float* frame_1,
   return flow2d_synchronize(h);
 }
 
+// ---- one large frame on several GPUs ---------------------------------------------------------------------------
+static int slab_alloc_mailbox(flow2d_handle* h) {
+  if (h->mailbox) return FLOW2D_OK;
+  h->mailbox_rows = kSlabRowsCap;
+  h->mailbox_bytes = kSlabHeaderBytes + (size_t)8 * h->mailbox_rows * h->pitch * sizeof(float);  // 2 senders x 2 epochs x 2 fields
+  if (cudaMalloc(&h->mailbox, h->mailbox_bytes) != cudaSuccess || cudaMalloc(&h->slab_counter, 2 * sizeof(unsigned)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(h, FLOW2D_ERR_OUT_OF_MEMORY, "slab mailbox allocation failed");
+  }
+  CU_TRY(h, cudaMemset(h->mailbox, 0, h->mailbox_bytes));
+  CU_TRY(h, cudaMemset(h->slab_counter, 0, 2 * sizeof(unsigned)));
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_mailbox(flow2d_handle* h, void** d_mailbox, size_t* bytes) {
+  STAGE_PROLOGUE(h);
+  TRY(slab_alloc_mailbox(h));
+  if (d_mailbox) *d_mailbox = h->mailbox;
+  if (bytes) *bytes = h->mailbox_bytes;
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_export(flow2d_handle* h, unsigned char ipc_handle[64]) {
+  STAGE_PROLOGUE(h);
+  if (!ipc_handle) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null handle buffer");
+  TRY(slab_alloc_mailbox(h));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t m;
+  CU_TRY(h, cudaIpcGetMemHandle(&m, h->mailbox));
+  std::memcpy(ipc_handle, &m, 64);
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_import(flow2d_handle* h, const unsigned char ipc_handle[64], void** d_mailbox) {
+  STAGE_PROLOGUE(h);
+  if (!ipc_handle || !d_mailbox) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null argument");
+  cudaIpcMemHandle_t m;
+  std::memcpy(&m, ipc_handle, 64);
+  void* ptr = nullptr;
+  CU_TRY(h, cudaIpcOpenMemHandle(&ptr, m, cudaIpcMemLazyEnablePeerAccess));
+  for (auto& slot : h->imported)
+    if (!slot) { slot = ptr; break; }
+  *d_mailbox = ptr;
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_connect(flow2d_handle* h, int rank, int world, void* mailbox_above, void* mailbox_below, size_t min_rows_per_rank) {
+  STAGE_PROLOGUE(h);
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "bad slab rank %d of %d", rank, world);
+  if (world > 1 && ((rank > 0 && !mailbox_above) || (rank < world - 1 && !mailbox_below)))
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "slab: rank %d of %d needs the mailboxes of its neighbours", rank, world);
+  TRY(slab_alloc_mailbox(h));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemset(h->mailbox, 0, kSlabHeaderBytes));  // flags start at epoch 0 (every rank connects before anyone computes)
+  CU_TRY(h, cudaMemset(h->slab_counter, 0, 2 * sizeof(unsigned)));
+  h->slab_rank = rank; h->slab_world = world;
+  h->slab_min_rows = min_rows_per_rank ? min_rows_per_rank : 128;
+  // same process, another device: the neighbour's mailbox must be mapped into this device (IPC imports already are)
+  for (void* m : {mailbox_above, mailbox_below}) {
+    if (!m) continue;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, m) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != h->device) {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(h, FLOW2D_ERR_CUDA, "slab: no peer access from device %d to device %d: %s", h->device, at.device, cudaGetErrorString(e));
+    }
+    (void)cudaGetLastError();
+  }
+  h->peer[0] = static_cast<unsigned char*>(mailbox_above);
+  h->peer[1] = static_cast<unsigned char*>(mailbox_below);
+  h->slab_epoch = 0;
+  h->slab_exchanges = 0; h->slab_bytes_sent = 0;
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_rows(const flow2d_handle* h, size_t level_height, size_t* y0, size_t* y1) {
+  if (!h || !y0 || !y1 || level_height == 0) return FLOW2D_ERR_INVALID_ARGUMENT;
+  int a, b;
+  slab_own_rows((int)level_height, h->slab_rank, h->slab_world, &a, &b);
+  *y0 = (size_t)a; *y1 = (size_t)b;
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_stats(const flow2d_handle* h, long long* exchanges, long long* bytes_sent, int* levels_slabbed) {
+  if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
+  if (exchanges) *exchanges = h->slab_exchanges;
+  if (bytes_sent) *bytes_sent = h->slab_bytes_sent;
+  if (levels_slabbed) *levels_slabbed = h->slab_levels;
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_status(flow2d_handle* h) {
+  STAGE_PROLOGUE(h);
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (!h->slab_counter) return FLOW2D_OK;
+  unsigned err = 0;
+  CU_TRY(h, cudaMemcpyAsync(&err, h->slab_counter + 1, sizeof err, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (err) return fail(h, FLOW2D_ERR_CUDA, "slab: rank %d timed out waiting for halo rows of a neighbour (reconnect every rank)", h->slab_rank);
+  return FLOW2D_OK;
+}
+
 int flow2d_compute_slab_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, float* d_flow_u,
-                               float* d_flow_v, const flow2d_params* p, const flow2d_slab* slab) {
+                               float* d_flow_v, const flow2d_params* p) {
   if (!h) return FLOW2D_ERR_INVALID_ARGUMENT;
   if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "null image pointer");
-  if (!slab || slab->world < 1 || slab->rank < 0 || slab->rank >= slab->world || (slab->world > 1 && !slab->exchange))
-    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "bad slab description");
   TRY(check_aligned(h, "compute", {d_frame_0, d_frame_1, d_flow_u, d_flow_v}));
   CU_TRY(h, cudaSetDevice(h->device));
   reset_launch_counts(h);
-  return enqueue_pyramid(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p, slab);  // callbacks inside: no graph capture
+  return enqueue_pyramid(h, d_frame_0, d_frame_1, d_flow_u, d_flow_v, p, true);  // epochs are kernel arguments: no graph replay
 }
 
 int flow2d_stage_solve_slab(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, const float* d_flow_u,
                             const float* d_flow_v, float* d_flow_du, float* d_flow_dv, size_t w, size_t hh, float hx,
-                            float hy, const flow2d_params* p, const flow2d_slab* slab) {
+                            float hy, const flow2d_params* p, int* slabbed) {
   STAGE_PROLOGUE(h);
-  if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v || !d_flow_du || !d_flow_dv || !p || !slab)
+  if (!d_frame_0 || !d_frame_1 || !d_flow_u || !d_flow_v || !d_flow_du || !d_flow_dv || !p)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "solve: null argument");
-  if (slab->world < 1 || slab->rank < 0 || slab->rank >= slab->world || (slab->world > 1 && !slab->exchange))
-    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "bad slab description");
   if (p->sweeps_per_pass < 0 || p->sweeps_per_pass > FLOW2D_MAX_SWEEPS_PER_PASS)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "sweeps_per_pass must be 0..%d", FLOW2D_MAX_SWEEPS_PER_PASS);
   TRY(check_level(h, w, hh));
   TRY(check_aligned(h, "solve", {d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_flow_du, d_flow_dv}));
   const LevelGeom g = geom(h, w, hh, hx, hy);
   TRY(run_derivatives(h, g, d_frame_0, d_frame_1));
+  const SolvePlan pl = plan_solve(h, g, p, 1, true);
+  if (slabbed) *slabbed = pl.slabbed ? 1 : 0;
   return run_solve(h, g, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI],
-                   false, p, slab);
+                   false, p, pl);
 }
 
 // Debug aid (not part of the drop-in surface): solve_pass writes 8 globaltimer stamps per CTA of the
@@ -934,7 +1210,7 @@ int flow2d_stage_solve(flow2d_handle* h, const float* d_frame_0, const float* d_
   TRY(run_derivatives(h, g, d_frame_0, d_frame_1));
   const bool want_phi = d_phi != nullptr;
   return run_solve(h, g, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1],
-                   want_phi ? d_phi : h->c[C_PHI], want_phi ? d_ksi : h->c[C_KSI], want_phi, p);
+                   want_phi ? d_phi : h->c[C_PHI], want_phi ? d_ksi : h->c[C_KSI], want_phi, p, plan_solve(h, g, p, 1, false));
 }
 
 int flow2d_stage_add(flow2d_handle* h, float* d_a, const float* d_b, size_t w, size_t hh) {

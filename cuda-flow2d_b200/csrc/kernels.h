@@ -15,18 +15,21 @@ struct ResampleJob {
   float* tmp;
   float* out;
   int iw, ih, ow, oh;
+  int oy0, oy1;  // output rows to produce (oy1 <= oy0: all of them); row-slab mode
+  int iy0, iy1;  // filled in by the launcher: the input rows those output rows are made of
 };
 void launch_resample_batch(cudaStream_t st, const ResampleJob* jobs, int count, int pitch);
+// y0, y1: rows of the level to produce (y1 <= y0: all of them); row-slab mode
 void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float* u, const float* v, float* out,
-                 const LevelGeom& g);
+                 const LevelGeom& g, int y0 = 0, int y1 = 0);
 void launch_derivatives(cudaStream_t st, const float* f0, const float* f1w, float* fx, float* fy, float* ft,
-                        const LevelGeom& g);
+                        const LevelGeom& g, int y0 = 0, int y1 = 0);
 void launch_grad_tensor(cudaStream_t st, const float* fx, const float* fy, const float* ft, float* const* J,
-                        const LevelGeom& g);
+                        const LevelGeom& g, int y0 = 0, int y1 = 0);
 
 // ---- median.cu ----
 void launch_add_median(cudaStream_t st, const float* const* a, const float* const* b, float* const* out, int count,
-                       int w, int h, int pitch, int radius);
+                       int w, int h, int pitch, int radius, int row0 = 0, int row1 = 0);
 void launch_add(cudaStream_t st, float* a, const float* b, int w, int h, int pitch);
 
 // ---- solve.cu ----
@@ -71,6 +74,34 @@ void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int
 // whole solve of a level of <= 1024 pixels in one CTA, one thread per pixel (a.outer, a.sweeps = inner)
 bool solve_tiny_fits(int w, int h);
 void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad);
+
+// ---- slab.cu: halo exchange between neighbour GPUs through peer-mapped mailboxes ----
+struct SlabPushDir {
+  float* dst[2];                // receive buffers of the two fields in the neighbour's mailbox (peer mapping)
+  unsigned long long* flag;     // the neighbour's flag for messages from this side
+  unsigned long long epoch;
+  int row0, rows;               // rows [row0, row0 + rows) of the sender's containers; rows = 0: nothing to send
+};
+struct SlabPush {
+  const float* field[2];
+  SlabPushDir dir[2];           // 0: to the rank above, 1: to the rank below
+  unsigned* counter;            // sender-local, zero between launches
+  int w, pitch;
+};
+struct SlabUnpackDir {
+  const float* src[2];          // receive buffers in the own mailbox
+  const unsigned long long* flag;
+  unsigned long long epoch;     // wait until *flag >= epoch
+  int row0, rows;               // destination rows in the own containers
+};
+struct SlabUnpack {
+  float* field[2];
+  SlabUnpackDir dir[2];         // 0: from the rank above, 1: from the rank below
+  unsigned* error;              // set to 1 when a wait timed out (flow2d_slab_status)
+  int w, pitch;
+};
+void launch_slab_push(cudaStream_t st, const SlabPush& p);
+void launch_slab_unpack(cudaStream_t st, const SlabUnpack& p);
 
 // ---- residual.cu (opt-in diagnostics, not on the default path) ----
 struct ResidualJ { const float* p[5]; };

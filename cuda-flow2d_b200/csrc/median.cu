@@ -76,14 +76,14 @@ struct MedianPair {
 
 template <int R>
 __global__ void __launch_bounds__(kMedTW * kMedTH)
-add_median_kernel(MedianPair io, int w, int h, int pitch) {
+add_median_kernel(MedianPair io, int w, int h, int pitch, int row0, int row1) {
   constexpr int R2 = R / 2;
   constexpr int SW = kMedTW + 2 * R2, SH = kMedTH + 2 * R2;
   __shared__ float tile[SH * SW];
   const float* __restrict__ a = blockIdx.z ? io.a[1] : io.a[0];
   const float* __restrict__ b = blockIdx.z ? io.b[1] : io.b[0];
   float* __restrict__ out = blockIdx.z ? io.out[1] : io.out[0];
-  const int x0 = blockIdx.x * kMedTW, y0 = blockIdx.y * kMedTH;
+  const int x0 = blockIdx.x * kMedTW, y0 = row0 + blockIdx.y * kMedTH;  // rows [row0, row1) of the level (all unless slabbed)
   const int tid = threadIdx.y * kMedTW + threadIdx.x;
   for (int i = tid; i < SH * SW; i += kMedTW * kMedTH) {
     const int ly = i / SW, lx = i - ly * SW;
@@ -93,7 +93,7 @@ add_median_kernel(MedianPair io, int w, int h, int pitch) {
   }
   __syncthreads();
   const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x >= w || y >= h) return;
+  if (x >= w || y >= row1) return;
   if constexpr (R == 1) {
     out[(size_t)y * pitch + x] = tile[threadIdx.y * SW + threadIdx.x];
   } else {
@@ -108,7 +108,8 @@ add_median_kernel(MedianPair io, int w, int h, int pitch) {
 
 // radius: already normalised to 1, 3, 5 or 7.  count = 1 or 2 images.
 void launch_add_median(cudaStream_t st, const float* const* a, const float* const* b, float* const* out, int count,
-                       int w, int h, int pitch, int radius) {
+                       int w, int h, int pitch, int radius, int row0, int row1) {
+  if (row1 <= row0) { row0 = 0; row1 = h; }
   MedianPair io;
   for (int i = 0; i < 2; i++) {
     int k = i < count ? i : 0;
@@ -116,12 +117,12 @@ void launch_add_median(cudaStream_t st, const float* const* a, const float* cons
     io.b[i] = b ? b[k] : nullptr;
     io.out[i] = out[k];
   }
-  dim3 block(kMedTW, kMedTH), grid((w + kMedTW - 1) / kMedTW, (h + kMedTH - 1) / kMedTH, count);
+  dim3 block(kMedTW, kMedTH), grid((w + kMedTW - 1) / kMedTW, (row1 - row0 + kMedTH - 1) / kMedTH, count);
   switch (radius) {
-    case 1: add_median_kernel<1><<<grid, block, 0, st>>>(io, w, h, pitch); break;
-    case 3: add_median_kernel<3><<<grid, block, 0, st>>>(io, w, h, pitch); break;
-    case 5: add_median_kernel<5><<<grid, block, 0, st>>>(io, w, h, pitch); break;
-    default: add_median_kernel<7><<<grid, block, 0, st>>>(io, w, h, pitch); break;
+    case 1: add_median_kernel<1><<<grid, block, 0, st>>>(io, w, h, pitch, row0, row1); break;
+    case 3: add_median_kernel<3><<<grid, block, 0, st>>>(io, w, h, pitch, row0, row1); break;
+    case 5: add_median_kernel<5><<<grid, block, 0, st>>>(io, w, h, pitch, row0, row1); break;
+    default: add_median_kernel<7><<<grid, block, 0, st>>>(io, w, h, pitch, row0, row1); break;
   }
 }
 

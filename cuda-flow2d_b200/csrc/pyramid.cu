@@ -77,61 +77,117 @@ struct ResampleBatch {  // up to four images per launch (blockIdx.z), each with 
   ResampleJob job[4];
 };
 
+// One thread = four consecutive outputs along x (one float4 store; the y pass also reads float4 rows of the x-pass
+// result): four independent fma chains in flight per thread instead of one.  Every output is still the reference's
+// sequential chain value = fma(frac_j, in[left_i + j], value), j ascending, times the normalisation (its order is
+// part of the result).
+struct ResampleCell {
+  int left_i, n;
+  float left_f, right_f;
+};
+__device__ __forceinline__ ResampleCell resample_cell(int o, int in_n, float delta) {
+  ResampleCell c;
+  c.left_f = (float)o * delta;
+  c.right_f = (float)(o + 1) * delta;
+  c.left_i = (int)floorf(c.left_f);
+  c.n = min(in_n, (int)ceilf(c.right_f)) - c.left_i;
+  return c;
+}
+__device__ __forceinline__ float resample_frac(const ResampleCell& c, int j, float delta) {
+  float frac = 1.f;
+  if (j == 0) frac = (float)(c.left_i + 1) - c.left_f;
+  if (j == c.n - 1) frac = c.right_f - (float)(c.left_i + j);
+  if (c.n == 1) frac = delta;
+  return frac;
+}
+
 template <bool ALONG_X>
 __global__ void __launch_bounds__(256)
 resample_kernel(ResampleBatch b, int pitch) {
   const ResampleJob& jb = b.job[blockIdx.z];
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  // out_w x out_h = what this pass writes; in_n -> out_n along the pass direction
-  const int out_w = jb.ow, out_h = ALONG_X ? jb.ih : jb.oh;
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  // rows this pass writes: the x pass the input rows [iy0, iy1) the y pass will read, the y pass the output rows [oy0, oy1)
+  const int y = (ALONG_X ? jb.iy0 : jb.oy0) + blockIdx.y * blockDim.y + threadIdx.y;
+  const int out_w = jb.ow, y_end = ALONG_X ? jb.iy1 : jb.oy1;
   const int in_n = ALONG_X ? jb.iw : jb.ih, out_n = ALONG_X ? jb.ow : jb.oh;
-  if (x >= out_w || y >= out_h) return;
+  if (x >= out_w || y >= y_end) return;
   const float* __restrict__ in = ALONG_X ? jb.in : jb.tmp;
   float* __restrict__ out = ALONG_X ? jb.tmp : jb.out;
-  const int o = ALONG_X ? x : y;
   const float delta = (float)in_n / (float)out_n;
   const float normalization = (float)out_n / (float)in_n;
-  const float left_f = (float)o * delta;
-  const float right_f = (float)(o + 1) * delta;
-  const int left_i = (int)floorf(left_f);
-  const int right_i = min(in_n, (int)ceilf(right_f));
-  const int n = right_i - left_i;
-  const float* src = ALONG_X ? in + (size_t)y * pitch + left_i : in + (size_t)left_i * pitch + x;
-  const size_t stride = ALONG_X ? 1 : (size_t)pitch;
-  float value = 0.f;
-  for (int j = 0; j < n; j++) {
-    float frac = 1.f;
-    if (j == 0) frac = (float)(left_i + 1) - left_f;
-    if (j == n - 1) frac = right_f - (float)(left_i + j);
-    if (n == 1) frac = delta;
-    value = fmaf(frac, src[j * stride], value);
+  float value[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ALONG_X) {
+    const float* row = in + (size_t)y * pitch;
+    ResampleCell c[4];
+    int nmax = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      c[i] = resample_cell(min(x + i, out_w - 1), in_n, delta);
+      nmax = max(nmax, c[i].n);
+    }
+    for (int j = 0; j < nmax; j++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (j < c[i].n) value[i] = fmaf(resample_frac(c[i], j, delta), row[c[i].left_i + j], value[i]);
+    }
+  } else {
+    const ResampleCell c = resample_cell(y, in_n, delta);
+    const float* src = in + (size_t)c.left_i * pitch + x;
+    if (x + 3 < out_w) {
+      for (int j = 0; j < c.n; j++) {
+        const float frac = resample_frac(c, j, delta);
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)j * pitch);
+        value[0] = fmaf(frac, v.x, value[0]);
+        value[1] = fmaf(frac, v.y, value[1]);
+        value[2] = fmaf(frac, v.z, value[2]);
+        value[3] = fmaf(frac, v.w, value[3]);
+      }
+    } else {
+      for (int j = 0; j < c.n; j++) {
+        const float frac = resample_frac(c, j, delta);
+        for (int i = 0; x + i < out_w; i++) value[i] = fmaf(frac, src[(size_t)j * pitch + i], value[i]);
+      }
+    }
   }
-  out[(size_t)y * pitch + x] = value * normalization;
+  float* o = out + (size_t)y * pitch + x;
+  if (x + 3 < out_w) {
+    *reinterpret_cast<float4*>(o) = make_float4(value[0] * normalization, value[1] * normalization, value[2] * normalization,
+                                                value[3] * normalization);
+  } else {
+    for (int i = 0; x + i < out_w; i++) o[i] = value[i] * normalization;
+  }
 }
 
-// One x pass and one y pass for `count` (1..4) images of possibly different sizes.
+// One x pass and one y pass for `count` (1..4) images of possibly different sizes.  A job with oy0 < oy1 < oh produces
+// only those output rows (row-slab mode): the x pass then covers just the input rows they are made of.
 void launch_resample_batch(cudaStream_t st, const ResampleJob* jobs, int count, int pitch) {
   ResampleBatch b;
   int gw = 0, gh_x = 0, gh_y = 0;
   for (int i = 0; i < 4; i++) {
-    b.job[i] = jobs[i < count ? i : 0];
+    ResampleJob& j = b.job[i];
+    j = jobs[i < count ? i : 0];
+    if (j.oy1 <= j.oy0) { j.oy0 = 0; j.oy1 = j.oh; }  // default: all rows
+    // input rows [iy0, iy1) that the output rows [oy0, oy1) read: same fp32 expressions as the kernel
+    const float delta = (float)j.ih / (float)j.oh;
+    j.iy0 = (int)floorf((float)j.oy0 * delta);
+    const int hi = (int)ceilf((float)j.oy1 * delta);
+    j.iy1 = hi < j.ih ? hi : j.ih;
     if (i < count) {
-      gw = jobs[i].ow > gw ? jobs[i].ow : gw;
-      gh_x = jobs[i].ih > gh_x ? jobs[i].ih : gh_x;
-      gh_y = jobs[i].oh > gh_y ? jobs[i].oh : gh_y;
+      gw = j.ow > gw ? j.ow : gw;
+      gh_x = j.iy1 - j.iy0 > gh_x ? j.iy1 - j.iy0 : gh_x;
+      gh_y = j.oy1 - j.oy0 > gh_y ? j.oy1 - j.oy0 : gh_y;
     }
   }
   dim3 block(32, 8);
-  resample_kernel<true><<<dim3((gw + 31) / 32, (gh_x + 7) / 8, count), block, 0, st>>>(b, pitch);
-  resample_kernel<false><<<dim3((gw + 31) / 32, (gh_y + 7) / 8, count), block, 0, st>>>(b, pitch);
+  resample_kernel<true><<<dim3((gw + 127) / 128, (gh_x + 7) / 8, count), block, 0, st>>>(b, pitch);
+  resample_kernel<false><<<dim3((gw + 127) / 128, (gh_y + 7) / 8, count), block, 0, st>>>(b, pitch);
 }
 
 // (iw x ih) -> (ow x oh) for `count` (1 or 2) images; tmp[] are scratch containers.
 void launch_resample(cudaStream_t st, const float* const* in, float* const* tmp, float* const* out, int count,
                      int iw, int ih, int ow, int oh, int pitch) {
   ResampleJob jobs[2];
-  for (int i = 0; i < count && i < 2; i++) jobs[i] = ResampleJob{in[i], tmp[i], out[i], iw, ih, ow, oh};
+  for (int i = 0; i < count && i < 2; i++) jobs[i] = ResampleJob{in[i], tmp[i], out[i], iw, ih, ow, oh, 0, 0, 0, 0};
   launch_resample_batch(st, jobs, count < 2 ? count : 2, pitch);
 }
 
@@ -176,10 +232,10 @@ __device__ __forceinline__ float warp_blend(const WarpTap& t, float f00, float f
 // One thread = four consecutive pixels: float4 loads of u, v, one float4 store, 16 gathers in flight.
 __global__ void __launch_bounds__(256)
 warp_kernel(const float* __restrict__ f0, const float* __restrict__ f1, const float* __restrict__ u,
-            const float* __restrict__ v, float* __restrict__ out, int w, int h, int pitch, float rhx, float rhy) {
+            const float* __restrict__ v, float* __restrict__ out, int w, int h, int pitch, float rhx, float rhy, int y0, int y1) {
   const int xx = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int yy = blockIdx.y * blockDim.y + threadIdx.y;
-  if (xx >= w || yy >= h) return;
+  const int yy = y0 + blockIdx.y * blockDim.y + threadIdx.y;  // rows [y0, y1) of the level (all of them unless slabbed)
+  if (xx >= w || yy >= y1) return;
   const int c = yy * pitch + xx;
   const float bx = (float)(w - 1), by = (float)(h - 1);
   if (xx + 3 < w) {
@@ -206,9 +262,10 @@ warp_kernel(const float* __restrict__ f0, const float* __restrict__ f1, const fl
 }
 
 void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float* u, const float* v, float* out,
-                 const LevelGeom& g) {
-  dim3 block(32, 8), grid((g.w + 127) / 128, (g.h + 7) / 8);
-  warp_kernel<<<grid, block, 0, st>>>(f0, f1, u, v, out, g.w, g.h, g.pitch, 1.f / g.hx, 1.f / g.hy);
+                 const LevelGeom& g, int y0, int y1) {
+  if (y1 <= y0) { y0 = 0; y1 = g.h; }
+  dim3 block(32, 8), grid((g.w + 127) / 128, (y1 - y0 + 7) / 8);
+  warp_kernel<<<grid, block, 0, st>>>(f0, f1, u, v, out, g.w, g.h, g.pitch, 1.f / g.hx, 1.f / g.hy, y0, y1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,11 +277,11 @@ void launch_warp(cudaStream_t st, const float* f0, const float* f1, const float*
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 derivatives_kernel(const float* __restrict__ f0, const float* __restrict__ f1, float* __restrict__ fx,
-                   float* __restrict__ fy, float* __restrict__ ft, int w, int h, int pitch, float hx4, float hy4) {
+                   float* __restrict__ fy, float* __restrict__ ft, int w, int h, int pitch, float hx4, float hy4, int y0, int y1) {
   // one thread = four consecutive pixels (float4 rows; the two x neighbours outside the strip are scalar loads)
   const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= w || y >= h) return;
+  const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= y1) return;
   const int ym = mirror_clamp(y - 1, h), yp = mirror_clamp(y + 1, h);
   const size_t row = (size_t)y * pitch, up = (size_t)ym * pitch, dn = (size_t)yp * pitch;
   if (x + 3 < w) {
@@ -265,10 +322,10 @@ derivatives_kernel(const float* __restrict__ f0, const float* __restrict__ f1, f
 __global__ void __launch_bounds__(256)
 grad_tensor_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ ft,
                    float* __restrict__ J11, float* __restrict__ J22, float* __restrict__ J12,
-                   float* __restrict__ J13, float* __restrict__ J23, int w, int h, int pitch, float hx_1, float hy_1) {
+                   float* __restrict__ J13, float* __restrict__ J23, int w, int h, int pitch, float hx_1, float hy_1, int y0, int y1) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= w || y >= h) return;
+  const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= y1) return;
   const int tx = x & 15, ty = y & 7;
   const int xl = (tx == 0) ? x : x - 1;
   const int xr = (tx == 15 || x + 1 >= w) ? x : x + 1;
@@ -289,16 +346,18 @@ grad_tensor_kernel(const float* __restrict__ fx, const float* __restrict__ fy, c
 }
 
 void launch_derivatives(cudaStream_t st, const float* f0, const float* f1w, float* fx, float* fy, float* ft,
-                        const LevelGeom& g) {
-  dim3 block(32, 8), grid((g.w + 127) / 128, (g.h + 7) / 8);
-  derivatives_kernel<<<grid, block, 0, st>>>(f0, f1w, fx, fy, ft, g.w, g.h, g.pitch, g.hx * 4.f, g.hy * 4.f);
+                        const LevelGeom& g, int y0, int y1) {
+  if (y1 <= y0) { y0 = 0; y1 = g.h; }
+  dim3 block(32, 8), grid((g.w + 127) / 128, (y1 - y0 + 7) / 8);
+  derivatives_kernel<<<grid, block, 0, st>>>(f0, f1w, fx, fy, ft, g.w, g.h, g.pitch, g.hx * 4.f, g.hy * 4.f, y0, y1);
 }
 
 void launch_grad_tensor(cudaStream_t st, const float* fx, const float* fy, const float* ft, float* const* J,
-                        const LevelGeom& g) {
-  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
+                        const LevelGeom& g, int y0, int y1) {
+  if (y1 <= y0) { y0 = 0; y1 = g.h; }
+  dim3 block(32, 8), grid((g.w + 31) / 32, (y1 - y0 + 7) / 8);
   const float hx_1 = (float)(1.0 / (2.0 * (double)g.hx)), hy_1 = (float)(1.0 / (2.0 * (double)g.hy));
-  grad_tensor_kernel<<<grid, block, 0, st>>>(fx, fy, ft, J[0], J[1], J[2], J[3], J[4], g.w, g.h, g.pitch, hx_1, hy_1);
+  grad_tensor_kernel<<<grid, block, 0, st>>>(fx, fy, ft, J[0], J[1], J[2], J[3], J[4], g.w, g.h, g.pitch, hx_1, hy_1, y0, y1);
 }
 
 }  // namespace flow2d

@@ -193,35 +193,47 @@ FLOW2D_API int flow2d_stage_median(flow2d_handle* h, const float* d_in, float* d
 FLOW2D_API int flow2d_stage_add_median(flow2d_handle* h, const float* d_a, const float* d_b, float* d_out,
                             size_t w, size_t h_, size_t radius);
 
-/* ---- one large frame on several GPUs: row-slab decomposition of the solve ----------------------
- * (no counterpart upstream: the reference is single-GPU; SURVEY.md 8e, BASELINE.json configs[4]).
- * One process / handle per GPU, every rank holds both full frames.  Pyramid levels with at least
- * min_rows_per_rank rows per rank are slabbed: each rank runs the solve passes (99 % of the work)
- * only on its own rows plus `ghost` rows on either side, exchanging ghost rows of the increment with
- * its two neighbours every few outer iterations and gathering the increment at the end of the level.
- * Everything else (restriction, warp, derivatives, add + median, the small levels) is computed
- * redundantly by every rank.  The Jacobi scheme makes the result bit-identical to a single GPU.
- * The transport is the caller's: `exchange` is called on the host, in stream order of the handle's
- * stream, with
- *   op 0 (halo):   send rows [own_y0, own_y0+ghost) to rank-1 and [own_y1-ghost, own_y1) to rank+1,
- *                  receive rows [own_y0-ghost, own_y0) from rank-1 and [own_y1, own_y1+ghost) from rank+1
- *   op 1 (gather): afterwards every rank must hold rows [0, height) of both fields; rank r contributes
- *                  rows [r*b + min(r,e), ...) with b = height / world, e = height % world (+1 row for r < e)
- * for the two device containers d_du, d_dv (row pitch pitch_elems floats).  It returns 0 on success. */
-typedef int (*flow2d_slab_exchange_fn)(void* user, int op, float* d_du, float* d_dv, size_t pitch_elems,
-                                       size_t width, size_t height, size_t own_y0, size_t own_y1, size_t ghost);
-typedef struct flow2d_slab {
-  int rank, world;
-  flow2d_slab_exchange_fn exchange;
-  void* user;
-  size_t min_rows_per_rank;  /* 0 = default (128) */
-} flow2d_slab;
+/* ---- one large frame on several GPUs: row-slab decomposition -------------------------------------------
+ * (no counterpart upstream: the reference is single-GPU, cuda_operation_solve_2d.cpp:168; SURVEY.md 8e,
+ * BASELINE.json configs[4]).  One handle per GPU (one process each, or several in one process); every rank holds
+ * both full frames.  Pyramid levels with at least min_rows_per_rank rows per rank are slabbed: a rank then computes
+ * its own rows of EVERY stage of the level (prolongation, warp, derivatives, robust iterations, add + median) plus
+ * the few rows of margin the next stage reads, and only rows of neighbours ever move:
+ *   - ghost rows of the increment (du, dv), refreshed from the two neighbour ranks every few outer iterations (a solve
+ *     pass with S sweeps is exact S+1 rows less far from a cut edge than its input was), and
+ *   - once per level, the rows of the new flow (u, v) that the neighbours' prolongation to the next level reads.
+ * The smaller levels and the restriction of the two frames are computed by every rank.  The Jacobi scheme makes the
+ * result bit-identical to a single GPU.
+ * Transport: each handle owns a MAILBOX in device memory; the neighbours write rows straight into it over NVLink
+ * (peer-mapped stores from a copy kernel) followed by a system-scope flag, and the receiver's stream waits for the
+ * flag in a kernel.  No host synchronisation, no collective library on the data path.  Wiring:
+ *   same process:   flow2d_slab_mailbox() of the neighbours' handles (the library enables peer access on connect)
+ *   one process per GPU: flow2d_slab_export() -> 64 bytes to the neighbours (any channel) -> flow2d_slab_import()
+ * then flow2d_slab_connect() on every rank, then flow2d_compute_slab_device() on every rank (each on its own host
+ * thread / process: a rank's stream waits for its neighbours' kernels).  On return (after the stream has drained) rows
+ * [y0, y1) = flow2d_slab_rows(handle, height) of d_flow_u / d_flow_v hold this rank's part of the flow. */
+FLOW2D_API int flow2d_slab_mailbox(flow2d_handle* h, void** d_mailbox, size_t* bytes);
+FLOW2D_API int flow2d_slab_export(flow2d_handle* h, unsigned char ipc_handle[64]);
+FLOW2D_API int flow2d_slab_import(flow2d_handle* h, const unsigned char ipc_handle[64], void** d_mailbox);
+/* mailbox_above = mailbox of rank-1 (NULL for rank 0), mailbox_below = mailbox of rank+1 (NULL for the last rank), both
+ * as addresses valid on this handle's device.  min_rows_per_rank: 0 = default (128).  world = 1 switches slabbing off. */
+FLOW2D_API int flow2d_slab_connect(flow2d_handle* h, int rank, int world, void* mailbox_above, void* mailbox_below,
+                        size_t min_rows_per_rank);
+FLOW2D_API int flow2d_slab_rows(const flow2d_handle* h, size_t level_height, size_t* y0, size_t* y1);
+/* exchanges and payload bytes sent by this rank since flow2d_slab_connect; levels slabbed in the last compute */
+FLOW2D_API int flow2d_slab_stats(const flow2d_handle* h, long long* exchanges, long long* bytes_sent, int* levels_slabbed);
 FLOW2D_API int flow2d_compute_slab_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
-                               float* d_flow_u, float* d_flow_v, const flow2d_params* p, const flow2d_slab* slab);
-/* flow2d_stage_solve on a slabbed level (for tests of the decomposition). */
+                               float* d_flow_u, float* d_flow_v, const flow2d_params* p);
+/* Waits for the handle's stream; FLOW2D_ERR_CUDA if a wait for a neighbour's rows gave up after 20 s (a rank that never
+ * sent: the results of this and the neighbouring ranks are then invalid and every rank must connect again).  Host code
+ * that drives several ranks from one process must not synchronise the whole DEVICE while ranks are in flight: a rank's
+ * stream waits for kernels its neighbours may not have enqueued yet. */
+FLOW2D_API int flow2d_slab_status(flow2d_handle* h);
+/* flow2d_stage_solve on a slabbed level (all inputs complete on every rank; the result is exact on the rank's own rows
+ * of the level +- median_radius / 2).  *slabbed tells whether the level was large enough to be slabbed. */
 FLOW2D_API int flow2d_stage_solve_slab(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1,
                             const float* d_flow_u, const float* d_flow_v, float* d_flow_du, float* d_flow_dv,
-                            size_t w, size_t h_, float hx, float hy, const flow2d_params* p, const flow2d_slab* slab);
+                            size_t w, size_t h_, float hx, float hy, const flow2d_params* p, int* slabbed);
 
 /* Debug aid, not part of the drop-in surface: every solve_pass CTA writes 8 %globaltimer stamps
  * (entry, loads+tensor, phi, weights, sweeps, stores) into d_stamps (device memory, >= 8 * CTAs of the
