@@ -73,7 +73,7 @@ struct flow2d_handle {
   int sm_count = 148;
   // row-slab decomposition (flow2d_slab_connect): this handle is rank `slab_rank` of `slab_world`
   int slab_rank = 0, slab_world = 1;
-  size_t slab_min_rows = 128;
+  size_t slab_min_rows = 64;
   unsigned char* mailbox = nullptr;          // own mailbox (its own cudaMalloc: CUDA IPC exports whole allocations)
   size_t mailbox_bytes = 0, mailbox_rows = 0;
   unsigned char* peer[2] = {nullptr, nullptr};  // mapped mailboxes of rank-1 (above) and rank+1 (below)
@@ -377,7 +377,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
     return check_launch(h, FLOW2D_K_SOLVE_RESIDENT, 1);
   }
 
-  const int S = pl.S, npass = pl.npass;
+  const int npass = pl.npass;
   const long long total = (long long)outer * npass;
   float* bufs[2][2] = {{du_a, dv_a}, {du_b, dv_b}};
   long long pass = 0;
@@ -572,16 +572,16 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     int njobs = 0;
     if (level != 0) {
       // (frame 1 is needed wherever the flow may point: all rows; frame 0 on the rows that are warped / differentiated)
-      jobs[njobs++] = ResampleJob{frame[0], h->c[C_TMP0], h->c[C_RES0], (int)W, (int)H, g.w, g.h, W0, W1, 0, 0};
-      jobs[njobs++] = ResampleJob{frame[1], h->c[C_TMP1], h->c[C_RES1], (int)W, (int)H, g.w, g.h, 0, 0, 0, 0};
+      jobs[njobs++] = ResampleJob{frame[0], h->c[C_TMP0], h->c[C_RES0], (int)W, (int)H, g.w, g.h, W0, W1, 0, 0, 0};
+      jobs[njobs++] = ResampleJob{frame[1], h->c[C_TMP1], h->c[C_RES1], (int)W, (int)H, g.w, g.h, 0, 0, 0, 0, 0};
       fr[0] = h->c[C_RES0]; fr[1] = h->c[C_RES1];
     }
     if (pw == 0) {
       CU_TRY(h, cudaMemset2DAsync(u, h->pitch * 4, 0, cw * 4, ch, st));
       CU_TRY(h, cudaMemset2DAsync(v, h->pitch * 4, 0, cw * 4, ch, st));
     } else {
-      jobs[njobs++] = ResampleJob{u, h->c[C_DU1], u2, (int)pw, (int)ph, g.w, g.h, W0, W1, 0, 0};
-      jobs[njobs++] = ResampleJob{v, h->c[C_DV1], v2, (int)pw, (int)ph, g.w, g.h, W0, W1, 0, 0};
+      jobs[njobs++] = ResampleJob{u, h->c[C_DU1], u2, (int)pw, (int)ph, g.w, g.h, W0, W1, 0, 0, 0};
+      jobs[njobs++] = ResampleJob{v, h->c[C_DV1], v2, (int)pw, (int)ph, g.w, g.h, W0, W1, 0, 0, 0};
       std::swap(u, u2); std::swap(v, v2);
     }
     if (njobs) {
@@ -1074,7 +1074,7 @@ int flow2d_slab_connect(flow2d_handle* h, int rank, int world, void* mailbox_abo
   CU_TRY(h, cudaMemset(h->mailbox, 0, kSlabHeaderBytes));  // flags start at epoch 0 (every rank connects before anyone computes)
   CU_TRY(h, cudaMemset(h->slab_counter, 0, 2 * sizeof(unsigned)));
   h->slab_rank = rank; h->slab_world = world;
-  h->slab_min_rows = min_rows_per_rank ? min_rows_per_rank : 128;
+  h->slab_min_rows = min_rows_per_rank ? min_rows_per_rank : 64;
   // same process, another device: the neighbour's mailbox must be mapped into this device (IPC imports already are)
   for (void* m : {mailbox_above, mailbox_below}) {
     if (!m) continue;

@@ -17,6 +17,7 @@ struct ResampleJob {
   int iw, ih, ow, oh;
   int oy0, oy1;  // output rows to produce (oy1 <= oy0: all of them); row-slab mode
   int iy0, iy1;  // filled in by the launcher: the input rows those output rows are made of
+  int chunk;     // filled in by the launcher: outputs per CTA of the staged x pass
 };
 void launch_resample_batch(cudaStream_t st, const ResampleJob* jobs, int count, int pitch);
 // y0, y1: rows of the level to produce (y1 <= y0: all of them); row-slab mode

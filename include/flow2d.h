@@ -216,7 +216,7 @@ FLOW2D_API int flow2d_slab_mailbox(flow2d_handle* h, void** d_mailbox, size_t* b
 FLOW2D_API int flow2d_slab_export(flow2d_handle* h, unsigned char ipc_handle[64]);
 FLOW2D_API int flow2d_slab_import(flow2d_handle* h, const unsigned char ipc_handle[64], void** d_mailbox);
 /* mailbox_above = mailbox of rank-1 (NULL for rank 0), mailbox_below = mailbox of rank+1 (NULL for the last rank), both
- * as addresses valid on this handle's device.  min_rows_per_rank: 0 = default (128).  world = 1 switches slabbing off. */
+ * as addresses valid on this handle's device.  min_rows_per_rank: 0 = default (64; a level also needs twice the ghost rows per rank).  world = 1 switches slabbing off. */
 FLOW2D_API int flow2d_slab_connect(flow2d_handle* h, int rank, int world, void* mailbox_above, void* mailbox_below,
                         size_t min_rows_per_rank);
 FLOW2D_API int flow2d_slab_rows(const flow2d_handle* h, size_t level_height, size_t* y0, size_t* y1);
