@@ -766,7 +766,7 @@ const char* flow2d_version(void) { return "flow2d-b200 0.1.0 sm_100a"; }
 
 void* flow2d_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
     (void)cudaGetLastError();
     return nullptr;
   }

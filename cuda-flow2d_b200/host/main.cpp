@@ -41,6 +41,20 @@ static int run_sequence(int argc, char** argv) {
     const string a = argv[i];
     if (a == "--handles" && i + 1 < argc) opt.handles = std::atoi(argv[++i]);
     else if (a == "--device" && i + 1 < argc) opt.device = std::atoi(argv[++i]);
+    else if (a == "--devices" && i + 1 < argc) {  // "0-7", "0,2,5", "0-3,6"
+      const string spec = argv[++i];
+      size_t pos_ = 0;
+      while (pos_ < spec.size()) {
+        size_t end = spec.find(',', pos_);
+        if (end == string::npos) end = spec.size();
+        const string part = spec.substr(pos_, end - pos_);
+        const size_t dash = part.find('-');
+        const int lo = std::atoi(part.substr(0, dash).c_str());
+        const int hi = dash == string::npos ? lo : std::atoi(part.substr(dash + 1).c_str());
+        for (int d = lo; d <= hi && d - lo < 64; d++) opt.devices.push_back(d);
+        pos_ = end + 1;
+      }
+    } else if (a == "--io-threads" && i + 1 < argc) opt.io_threads = std::atoi(argv[++i]);
     else if (a == "--u8") type = FlowSequence::PixelType::U8;
     else if (a == "--f32") type = FlowSequence::PixelType::F32;
     else if (a == "--color") opt.write_color = true;
@@ -73,7 +87,8 @@ static int run_sequence(int argc, char** argv) {
   }
   if (pos.size() < 4) {
     std::cout << "Usage: " << argv[0] << " --sequence <width> <height> <output path> <frame 0> <frame 1> [...] | <directory> | <stack file>\n"
-              << "       [--handles K] [--u8|--f32] [--settings file] [--gradient] [--color] [--amp] [--no-flow] [--device D] [--list]"
+              << "       [--handles K] [--u8|--f32] [--settings file] [--gradient] [--color] [--amp] [--no-flow] [--device D | --devices 0-7]\n"
+              << "       [--io-threads T] [--list]     (K pairs in flight per GPU; pair i runs on GPU i mod N)"
               << std::endl;
     return 0;
   }
@@ -95,6 +110,7 @@ static int run_sequence(int argc, char** argv) {
   if (rc == 0) {
     std::printf("Sequence: %d frame pairs on %d concurrent handles in %.3f s: %.2f pairs/s, %.2f Mpix/s end to end\n", st.pairs,
                 st.handles, st.seconds, st.pairs / st.seconds, st.pairs * (double)width * height / st.seconds * 1e-6);
+    std::printf("Sequence: %d GPU(s), %d reader and %d writer thread(s)\n", st.gpus, st.io_threads, st.io_threads);
     std::printf("Sequence: reader busy %.3f s, writer busy %.3f s; scheduler waited %.3f s for frames, %.3f s for the GPU, %.3f s for the writer\n",
                 st.read_seconds, st.write_seconds, st.wait_frames_seconds, st.wait_gpu_seconds, st.wait_writer_seconds);
   }

@@ -128,32 +128,37 @@ bool FrameSource::Read(int i, float* dst) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pipeline.  Three threads and two rings of page-locked buffers:
-//   reader     frame j -> frame slot j % R          (may run R-K-1 frames ahead of the GPU)
-//   scheduler  pair i = (frame i, frame i+1) -> handle i % K, flow -> output slot i % M
-//   writer     output slot -> files
-// A frame slot is recycled when both pairs that read it are complete, an output slot when its
-// files are closed.  Everything is ordered by three monotone counters under one mutex.
+// Pipeline.  Reader threads, a scheduler, writer threads and two rings of page-locked buffers:
+//   readers    frame j -> frame slot j % R          (may run R-T-1 frames ahead of the GPUs)
+//   scheduler  pair i = (frame i, frame i+1) -> handle i % T, flow -> output slot i % M
+//   writers    output slot -> files
+// T = K handles on each of the N GPUs, handle t on GPU t % N, so pair i goes to GPU i mod N (independent units: nothing
+// moves between GPUs).  A frame slot is recycled when both pairs that read it are complete, an output slot when its
+// files are closed.  Everything is ordered by monotone counters (contiguous prefixes of per-item flags) under one mutex.
 // ---------------------------------------------------------------------------------------------
 int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, Stats* stats) {
   const int n_frames = source.Count(), n_pairs = n_frames - 1;
   if (n_pairs < 1) return 2;
   const size_t width = source.Width(), height = source.Height();
-  const int K = std::max(1, std::min(opt.handles, n_pairs));
-  const int R = K + 3, M = 2 * K;
+  std::vector<int> devices = opt.devices;
+  if (devices.empty()) devices.push_back(opt.device);
+  const int N = (int)devices.size();
+  const int T = std::max(1, std::min(std::max(1, opt.handles) * N, n_pairs));
+  const int R = T + 3 + N, M = 2 * T;
+  const int n_io = std::max(1, opt.io_threads > 0 ? opt.io_threads : (N + 1) / 2);
 
   // (throughput_mode stays as the caller set it: measured on B200 with 4-8 handles, the latency schedule of the
   // one-pixel kernels is also the better throughput schedule)
   flow2d_params p = opt.params;
 
-  std::vector<flow2d_handle*> handles(K, nullptr);
+  std::vector<flow2d_handle*> handles(T, nullptr);
   auto destroy_handles = [&]() {
     for (auto* h : handles)
       if (h) flow2d_destroy(h);
   };
-  for (int k = 0; k < K; k++)
-    if (flow2d_create(&handles[k], opt.device, (int)width, (int)height, opt.constancy) != FLOW2D_OK) {
-      std::fprintf(stderr, "Error: cannot create a flow2d handle on device %d (no sm_100 GPU?)\n", opt.device);
+  for (int k = 0; k < T; k++)
+    if (flow2d_create(&handles[k], devices[k % N], (int)width, (int)height, opt.constancy) != FLOW2D_OK) {
+      std::fprintf(stderr, "Error: cannot create a flow2d handle on device %d (no sm_100 GPU?)\n", devices[k % N]);
       destroy_handles();
       return 1;
     }
@@ -167,77 +172,96 @@ int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, 
 
   std::mutex mu;
   std::condition_variable cv;
+  std::vector<char> frame_ready(n_frames, 0), pair_written(n_pairs, 0);
   int loaded = 0;     // frames 0..loaded-1 are in their slots
   int completed = 0;  // pairs 0..completed-1 are off the GPU
   int written = 0;    // pairs 0..written-1 are on disk
-  int failure = 0;    // first error code; stops all three threads
+  int failure = 0;    // first error code; stops all threads
   std::deque<int> to_write;
   bool no_more_output = false;
   Stats st;
   st.pairs = n_pairs;
-  st.handles = K;
+  st.handles = T;
+  st.gpus = N;
+  st.io_threads = n_io;
   const double t_begin = now();
 
-  std::thread reader([&]() {
-    for (int j = 0; j < n_frames; j++) {
-      {
-        std::unique_lock<std::mutex> lk(mu);
-        // slot j % R held frame j-R, last read by pair j-R
-        cv.wait(lk, [&] { return failure || completed >= j - R + 1; });
-        if (failure) return;
+  // FrameSource::Read of a stack seeks in one FILE*: serialise the readers on it (files and directories read in parallel)
+  std::mutex stack_mu;
+  const bool serial_source = std::string(source.Kind()) == "stack";
+  std::vector<std::thread> readers, writers;
+  for (int rt = 0; rt < n_io; rt++)
+    readers.emplace_back([&, rt]() {
+      for (int j = rt; j < n_frames; j += n_io) {
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          // slot j % R held frame j-R, last read by pair j-R
+          cv.wait(lk, [&] { return failure || completed >= j - R + 1; });
+          if (failure) return;
+        }
+        const double t0 = now();
+        bool ok;
+        if (serial_source) {
+          std::lock_guard<std::mutex> g(stack_mu);
+          ok = source.Read(j, frames[j % R]->DataPtr());
+        } else {
+          ok = source.Read(j, frames[j % R]->DataPtr());
+        }
+        const double dt = now() - t0;
+        std::lock_guard<std::mutex> lk(mu);
+        st.read_seconds += dt;
+        if (!ok) {
+          std::fprintf(stderr, "%s\n", source.error.c_str());
+          if (!failure) failure = 2;
+        } else {
+          frame_ready[j] = 1;
+          while (loaded < n_frames && frame_ready[loaded]) ++loaded;
+        }
+        cv.notify_all();
+        if (!ok) return;
       }
-      const double t0 = now();
-      const bool ok = source.Read(j, frames[j % R]->DataPtr());
-      st.read_seconds += now() - t0;
-      std::lock_guard<std::mutex> lk(mu);
-      if (!ok) {
-        std::fprintf(stderr, "%s\n", source.error.c_str());
-        if (!failure) failure = 2;
-      } else {
-        loaded = j + 1;
-      }
-      cv.notify_all();
-      if (!ok) return;
-    }
-  });
+    });
 
   const std::string suffix = "-" + std::to_string(width) + "-" + std::to_string(height) + ".raw";
-  std::thread writer([&]() {
-    for (;;) {
-      int pair;
-      {
-        std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return failure || !to_write.empty() || no_more_output; });
-        if (failure || to_write.empty()) return;
-        pair = to_write.front();
-        to_write.pop_front();
+  for (int wt = 0; wt < n_io; wt++)
+    writers.emplace_back([&]() {
+      for (;;) {
+        int pair;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return failure || !to_write.empty() || no_more_output; });
+          if (failure || to_write.empty()) return;
+          pair = to_write.front();
+          to_write.pop_front();
+        }
+        const double t0 = now();
+        char tag[16];
+        std::snprintf(tag, sizeof tag, "%04d_", pair);
+        Data2D &u = *out_u[pair % M], &v = *out_v[pair % M];
+        bool ok = true;
+        if (opt.write_flow)
+          ok = u.WriteRAWToFileF32((out_prefix + tag + "flow-u" + suffix).c_str()) &&
+               v.WriteRAWToFileF32((out_prefix + tag + "flow-v" + suffix).c_str());
+        if (ok && opt.write_color) ok = IOUtils::WriteFlowToImageRGB(u, v, 10, out_prefix + tag + "res.pgm");  // src/main.cpp:212
+        if (ok && opt.write_amp) ok = IOUtils::WriteMagnitudeToFileF32(u, v, out_prefix + tag + "amp" + suffix);
+        const double dt = now() - t0;
+        std::lock_guard<std::mutex> lk(mu);
+        st.write_seconds += dt;
+        if (!ok && !failure) failure = 4;
+        pair_written[pair] = 1;
+        while (written < n_pairs && pair_written[written]) ++written;
+        cv.notify_all();
       }
-      const double t0 = now();
-      char tag[16];
-      std::snprintf(tag, sizeof tag, "%04d_", pair);
-      Data2D &u = *out_u[pair % M], &v = *out_v[pair % M];
-      bool ok = true;
-      if (opt.write_flow)
-        ok = u.WriteRAWToFileF32((out_prefix + tag + "flow-u" + suffix).c_str()) &&
-             v.WriteRAWToFileF32((out_prefix + tag + "flow-v" + suffix).c_str());
-      if (ok && opt.write_color) ok = IOUtils::WriteFlowToImageRGB(u, v, 10, out_prefix + tag + "res.pgm");  // src/main.cpp:212
-      if (ok && opt.write_amp) ok = IOUtils::WriteMagnitudeToFileF32(u, v, out_prefix + tag + "amp" + suffix);
-      st.write_seconds += now() - t0;
-      std::lock_guard<std::mutex> lk(mu);
-      if (!ok && !failure) failure = 4;
-      written = pair + 1;
-      cv.notify_all();
-    }
-  });
+    });
 
   // scheduler (this thread)
-  auto retire = [&](int pair) {  // pair is the oldest one still on the GPU
+  auto retire = [&](int pair) {  // pair is the oldest one still on the GPUs
     const double t0 = now();
-    const int rc = flow2d_synchronize(handles[pair % K]);
+    const int rc = flow2d_synchronize(handles[pair % T]);
     st.wait_gpu_seconds += now() - t0;
     std::lock_guard<std::mutex> lk(mu);
     if (rc != FLOW2D_OK) {
-      std::fprintf(stderr, "Error: %s\n", flow2d_last_error(handles[pair % K]));
+      std::fprintf(stderr, "Error: %s\n", flow2d_last_error(handles[pair % T]));
       if (!failure) failure = 1;
     } else {
       completed = pair + 1;
@@ -247,7 +271,7 @@ int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, 
   };
   int issued = 0;
   for (int i = 0; i < n_pairs; i++) {
-    if (i >= K) retire(i - K);
+    if (i >= T) retire(i - T);
     {
       std::unique_lock<std::mutex> lk(mu);
       double t0 = now();
@@ -258,7 +282,7 @@ int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, 
       st.wait_writer_seconds += now() - t0;
       if (failure) break;
     }
-    const int k = i % K;
+    const int k = i % T;
     if (flow2d_compute_async(handles[k], frames[i % R]->DataPtr(), frames[(i + 1) % R]->DataPtr(), out_u[i % M]->DataPtr(),
                              out_v[i % M]->DataPtr(), &p) != FLOW2D_OK) {
       std::fprintf(stderr, "Error: %s\n", flow2d_last_error(handles[k]));
@@ -269,14 +293,14 @@ int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, 
     }
     issued = i + 1;
   }
-  for (int i = std::max(0, issued - K); i < issued; i++) {
+  for (int i = std::max(0, issued - T); i < issued; i++) {
     bool stop;
     {
       std::lock_guard<std::mutex> lk(mu);
       stop = failure != 0;
     }
-    if (stop) {  // still drain the GPU before the buffers go away
-      flow2d_synchronize(handles[i % K]);
+    if (stop) {  // still drain the GPUs before the buffers go away
+      flow2d_synchronize(handles[i % T]);
       continue;
     }
     if (i >= completed) retire(i);
@@ -286,8 +310,8 @@ int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, 
     no_more_output = true;
     cv.notify_all();
   }
-  reader.join();
-  writer.join();
+  for (auto& t : readers) t.join();
+  for (auto& t : writers) t.join();
   st.seconds = now() - t_begin;
   destroy_handles();
   if (stats) *stats = st;

@@ -45,8 +45,10 @@ class FrameSource {
 };
 
 struct Options {
-  int handles = 4;            // frame pairs in flight on the GPU
+  int handles = 4;            // frame pairs in flight PER GPU
   int device = 0;
+  std::vector<int> devices;   // several GPUs: pair i -> GPU devices[i mod N] (empty = {device}); no data moves between GPUs
+  int io_threads = 0;         // reader threads and writer threads each; 0 = one per two GPUs
   int constancy = FLOW2D_GREY;
   bool write_color = false;   // NNNN_res.pgm  (src/utils/io_utils.cpp:140-225)
   bool write_amp = false;     // NNNN_amp-W-H.raw
@@ -55,9 +57,9 @@ struct Options {
 };
 
 struct Stats {
-  int pairs = 0, handles = 0;
+  int pairs = 0, handles = 0, gpus = 1, io_threads = 1;
   double seconds = 0;         // first read issued -> last file closed
-  double read_seconds = 0, write_seconds = 0;  // busy time of the two I/O threads
+  double read_seconds = 0, write_seconds = 0;  // busy time of the reader / writer threads (summed over the threads)
   double wait_frames_seconds = 0, wait_gpu_seconds = 0, wait_writer_seconds = 0;  // where the scheduler thread stalled
 };
 

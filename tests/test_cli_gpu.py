@@ -216,3 +216,28 @@ def test_failed_solve_is_not_reported_as_success(rub, tmp_path):
     r = _run(CLI, [], tmp_path)
     assert r.returncode not in (0, 1, 2, 3), r.stdout.decode()[-2000:]
     assert not (tmp_path / "out" / "flow-u-584-388.raw").exists()
+
+
+def test_sequence_on_several_devices(synth, oracle, tmp_path):
+    """--sequence --devices: pair i -> device list entry i mod N, K handles per entry, several reader / writer threads.
+    On a one-GPU box the list names device 0 twice (same scheduling code, two handle groups); with more GPUs the
+    driver's own multi-GPU run (tools/bench_sequence.py ... 0-7) covers the real thing.  Every pair equals the oracle."""
+    import torch
+    w, h, n = 96, 80, 9
+    (tmp_path / "out").mkdir()
+    frames = []
+    for i in range(n):
+        f, _, _, _ = synth.make_pair(w, h, 100, U0=(0.4 * i, -0.2 * i), U1=0.0)
+        frames.append(f)
+        f.tofile(tmp_path / ("frame%02d.raw" % i))
+    names = ["frame%02d.raw" % i for i in range(n)]
+    devs = "0-%d" % (min(torch.cuda.device_count(), 4) - 1) if torch.cuda.device_count() > 1 else "0,0"
+    r = _run(CLI, ["--sequence", w, h, "out/"] + names + ["--devices", devs, "--handles", 2, "--io-threads", 2], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    assert b"2 reader and 2 writer" in r.stdout
+    p = oracle.make_params()
+    for i in range(n - 1):
+        u = np.fromfile(tmp_path / "out" / ("%04d_flow-u-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+        v = np.fromfile(tmp_path / "out" / ("%04d_flow-v-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
+        ou, ov = oracle.compute_flow(frames[i], frames[i + 1], p)
+        assert np.all(u == ou) and np.all(v == ov), "pair %d" % i
