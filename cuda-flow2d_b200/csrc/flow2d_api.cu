@@ -12,6 +12,8 @@
 #include <new>
 #include <initializer_list>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/flow2d.h"
 #include "kernels.h"
@@ -1146,6 +1148,90 @@ int flow2d_stage_solve_slab(flow2d_handle* h, const float* d_frame_0, const floa
   if (slabbed) *slabbed = pl.slabbed ? 1 : 0;
   return run_solve(h, g, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI],
                    false, p, pl);
+}
+
+// ---- one large frame on several GPUs of one process: N handles, N host threads ----
+struct flow2d_slab_group {
+  std::vector<flow2d_handle*> h;
+  std::string err;
+};
+
+int flow2d_slab_group_create(flow2d_slab_group** out, const int* devices, int n, size_t width, size_t height, int constancy) {
+  if (!out || !devices || n < 1) return FLOW2D_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  flow2d_slab_group* g = new (std::nothrow) flow2d_slab_group;
+  if (!g) return FLOW2D_ERR_OUT_OF_MEMORY;
+  int rc = FLOW2D_OK;
+  for (int r = 0; r < n && rc == FLOW2D_OK; r++) {
+    flow2d_handle* hd = nullptr;
+    rc = flow2d_create(&hd, devices[r], width, height, constancy);
+    if (rc == FLOW2D_OK) g->h.push_back(hd);
+  }
+  std::vector<void*> box(n, nullptr);
+  for (int r = 0; r < n && rc == FLOW2D_OK; r++) rc = flow2d_slab_mailbox(g->h[r], &box[r], nullptr);
+  for (int r = 0; r < n && rc == FLOW2D_OK; r++)
+    rc = flow2d_slab_connect(g->h[r], r, n, r > 0 ? box[r - 1] : nullptr, r < n - 1 ? box[r + 1] : nullptr, 0);
+  if (rc != FLOW2D_OK) {
+    for (auto* hd : g->h) flow2d_destroy(hd);
+    delete g;
+    return rc;
+  }
+  *out = g;
+  return FLOW2D_OK;
+}
+
+int flow2d_slab_group_destroy(flow2d_slab_group* g) {
+  if (!g) return FLOW2D_OK;
+  for (auto* hd : g->h) flow2d_destroy(hd);
+  delete g;
+  return FLOW2D_OK;
+}
+
+const char* flow2d_slab_group_last_error(const flow2d_slab_group* g) { return g ? g->err.c_str() : "null group"; }
+
+int flow2d_slab_group_compute(flow2d_slab_group* g, const float* frame_0, const float* frame_1, float* flow_u, float* flow_v,
+                              const flow2d_params* p, float* device_ms) {
+  if (!g || !frame_0 || !frame_1 || !flow_u || !flow_v || !p) return FLOW2D_ERR_INVALID_ARGUMENT;
+  const int n = (int)g->h.size();
+  std::vector<int> rcs(n, FLOW2D_OK);
+  std::vector<float> ms(n, 0.f);
+  std::vector<std::thread> th;
+  for (int r = 0; r < n; r++)
+    th.emplace_back([&, r]() {
+      flow2d_handle* h = g->h[r];
+      auto run = [&]() -> int {
+        CU_TRY(h, cudaSetDevice(h->device));
+        const size_t row = h->W * sizeof(float), dpitch = h->pitch * sizeof(float);
+        cudaStream_t st = h->stream;
+        CU_TRY(h, cudaEventRecord(h->ev_start, st));
+        // every rank needs both frames completely (the warp reads rows it cannot know in advance)
+        CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN0], dpitch, frame_0, row, row, h->H, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN1], dpitch, frame_1, row, row, h->H, cudaMemcpyHostToDevice, st));
+        reset_launch_counts(h);
+        TRY(enqueue_pyramid(h, h->c[C_IN0], h->c[C_IN1], h->c[C_OUT_U], h->c[C_OUT_V], p, true));
+        size_t y0 = 0, y1 = 0;
+        flow2d_slab_rows(h, h->H, &y0, &y1);
+        // ... and returns its own rows of the flow
+        CU_TRY(h, cudaMemcpy2DAsync(flow_u + y0 * h->W, row, h->c[C_OUT_U] + y0 * h->pitch, dpitch, row, y1 - y0, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaMemcpy2DAsync(flow_v + y0 * h->W, row, h->c[C_OUT_V] + y0 * h->pitch, dpitch, row, y1 - y0, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaEventRecord(h->ev_stop, st));
+        TRY(flow2d_slab_status(h));
+        (void)cudaEventElapsedTime(&ms[r], h->ev_start, h->ev_stop);
+        return FLOW2D_OK;
+      };
+      rcs[r] = run();
+    });
+  for (auto& t : th) t.join();
+  float worst = 0.f;
+  for (int r = 0; r < n; r++) {
+    worst = ms[r] > worst ? ms[r] : worst;
+    if (rcs[r] != FLOW2D_OK) {
+      g->err = "rank " + std::to_string(r) + ": " + g->h[r]->err;
+      return rcs[r];
+    }
+  }
+  if (device_ms) *device_ms = worst;
+  return FLOW2D_OK;
 }
 
 // Debug aid (not part of the drop-in surface): solve_pass writes 8 globaltimer stamps per CTA of the

@@ -10,6 +10,8 @@
 //       flow between every pair of consecutive frames of a sequence, several pairs in flight at once
 //       (host/sequence.h); 8-bit / float32 frames told apart by file size; writes
 //       <out>NNNN_flow-u-W-H.raw / NNNN_flow-v-W-H.raw (and NNNN_res.pgm / NNNN_amp-W-H.raw on request)
+//   cuda-flow2d --slab <devices> <file1> <file2> <width> <height> <output path> [--gradient] [--settings file]   (new)
+//       one large frame pair on several GPUs (rows of the large levels split across them); bit-identical output
 //   any pair form + trailing --residuals                                                                   (new)
 //       prints the RMS residual of every level's last linear system (flow2d_level_residuals)
 // Differences: no getchar() at exit; 8-bit and float32 input files are told apart by their size (Mode@imageType only breaks ties);
@@ -29,6 +31,88 @@
 
 using std::string;
 
+// "0-7", "0,2,5", "0-3,6" -> device indices
+static std::vector<int> parse_devices(const string& spec) {
+  std::vector<int> out;
+  size_t pos = 0;
+  while (pos < spec.size()) {
+    size_t end = spec.find(',', pos);
+    if (end == string::npos) end = spec.size();
+    const string part = spec.substr(pos, end - pos);
+    const size_t dash = part.find('-');
+    const int lo = std::atoi(part.substr(0, dash).c_str());
+    const int hi = dash == string::npos ? lo : std::atoi(part.substr(dash + 1).c_str());
+    for (int d = lo; d <= hi && d - lo < 64; d++) out.push_back(d);
+    pos = end + 1;
+  }
+  return out;
+}
+
+static long long file_size(const string& p);
+
+// Slab mode: ONE large frame pair on several GPUs, rows of the large pyramid levels split across them
+// (flow2d_slab_group_*, include/flow2d.h; BASELINE.json configs[4]).  Same inputs, defaults and output files as the
+// <file1> <file2> <width> <height> <output path> form; the result is bit-identical to one GPU.
+static int run_slab(int argc, char** argv) {
+  if (argc < 8) {
+    std::cout << "Usage: " << argv[0] << " --slab <devices, e.g. 0-7> <file1> <file2> <width> <height> <output path> [--gradient] [--settings file]"
+              << std::endl;
+    return 0;
+  }
+  const std::vector<int> devices = parse_devices(argv[2]);
+  const string file1 = argv[3], file2 = argv[4], out = argv[7];
+  const size_t width = std::atoi(argv[5]), height = std::atoi(argv[6]);
+  flow2d_params p;
+  flow2d_default_params(&p);  // src/main.cpp:70-80
+  int constancy = FLOW2D_GREY;
+  for (int i = 8; i < argc; i++) {
+    const string a = argv[i];
+    if (a == "--gradient") constancy = FLOW2D_GRADIENT;
+    else if (a == "--settings" && i + 1 < argc) {
+      OpticFlow::Settings settings;
+      if (settings.LoadSettings(argv[++i]) != 0) {
+        std::cout << settings.error << std::endl;
+        return 3;
+      }
+      p.warp_levels_count = settings.levels; p.warp_scale_factor = settings.warpScale;
+      p.outer_iterations_count = settings.iterOuter; p.inner_iterations_count = settings.iterInner;
+      p.equation_alpha = settings.alpha; p.equation_data = settings.e_data; p.equation_smoothness = settings.e_smooth;
+      p.median_radius = settings.medianRadius; p.gaussian_sigma = settings.sigma;
+      if (settings.constancy == "gradient") constancy = FLOW2D_GRADIENT;
+    }
+  }
+  if (devices.empty() || width < 4 || height < 4) return 0;
+  Data2D frame_0, frame_1;
+  auto read_frame = [&](Data2D& d, const string& name) {
+    const bool u8 = file_size(name) == (long long)width * (long long)height;
+    return u8 ? d.ReadRAWFromFileU8(name.c_str(), width, height) : d.ReadRAWFromFileF32(name.c_str(), width, height);
+  };
+  if (!read_frame(frame_0, file1) || !read_frame(frame_1, file2)) return 2;
+  flow2d_slab_group* g = nullptr;
+  if (flow2d_slab_group_create(&g, devices.data(), (int)devices.size(), width, height, constancy) != FLOW2D_OK) {
+    std::cerr << "Error: cannot set up " << devices.size() << " GPUs for slab mode (sm_100 devices with peer access are needed)" << std::endl;
+    return 1;
+  }
+  Data2D flow_u(width, height), flow_v(width, height);
+  flow_u.ZeroData();
+  flow_v.ZeroData();
+  float ms = 0.f;
+  const int rc = flow2d_slab_group_compute(g, frame_0.DataPtr(), frame_1.DataPtr(), flow_u.DataPtr(), flow_v.DataPtr(), &p, &ms);
+  if (rc != FLOW2D_OK) {
+    std::cerr << "TERMINATING. " << flow2d_slab_group_last_error(g) << " (" << rc << ")" << std::endl;
+    flow2d_slab_group_destroy(g);
+    return 4;
+  }
+  flow2d_slab_group_destroy(g);
+  std::printf("Slab mode: %zu GPUs\nTotal GPU computation time: % 4.4fs\n", devices.size(), ms / 1000.);
+  const string suffix = "-" + std::to_string(width) + "-" + std::to_string(height) + ".raw";
+  bool written = flow_u.WriteRAWToFileF32((out + "flow-u" + suffix).c_str());
+  written = flow_v.WriteRAWToFileF32((out + "flow-v" + suffix).c_str()) && written;
+  IOUtils::WriteFlowToImageRGB(flow_u, flow_v, 10, out + "res.pgm");
+  IOUtils::WriteMagnitudeToFileF32(flow_u, flow_v, out + "amp" + suffix);
+  return written ? 0 : 5;
+}
+
 // Sequence mode: the X-ray-radiography use case of the reference README (one flow per consecutive
 // frame pair); host/sequence.{h,cpp} does the work.
 static int run_sequence(int argc, char** argv) {
@@ -41,19 +125,8 @@ static int run_sequence(int argc, char** argv) {
     const string a = argv[i];
     if (a == "--handles" && i + 1 < argc) opt.handles = std::atoi(argv[++i]);
     else if (a == "--device" && i + 1 < argc) opt.device = std::atoi(argv[++i]);
-    else if (a == "--devices" && i + 1 < argc) {  // "0-7", "0,2,5", "0-3,6"
-      const string spec = argv[++i];
-      size_t pos_ = 0;
-      while (pos_ < spec.size()) {
-        size_t end = spec.find(',', pos_);
-        if (end == string::npos) end = spec.size();
-        const string part = spec.substr(pos_, end - pos_);
-        const size_t dash = part.find('-');
-        const int lo = std::atoi(part.substr(0, dash).c_str());
-        const int hi = dash == string::npos ? lo : std::atoi(part.substr(dash + 1).c_str());
-        for (int d = lo; d <= hi && d - lo < 64; d++) opt.devices.push_back(d);
-        pos_ = end + 1;
-      }
+    else if (a == "--devices" && i + 1 < argc) {
+      opt.devices = parse_devices(argv[++i]);
     } else if (a == "--io-threads" && i + 1 < argc) opt.io_threads = std::atoi(argv[++i]);
     else if (a == "--u8") type = FlowSequence::PixelType::U8;
     else if (a == "--f32") type = FlowSequence::PixelType::F32;
@@ -138,6 +211,7 @@ int main(int argc, char** argv) {
   std::printf("//----------------------------------------------------------------------//\n");
 
   if (argc >= 2 && string(argv[1]) == "--sequence") return run_sequence(argc, argv);
+  if (argc >= 2 && string(argv[1]) == "--slab") return run_slab(argc, argv);
   // optional trailing flag of the pair forms (not in the reference): per-level residual norms on stdout
   bool report_residuals = false;
   if (argc >= 2 && string(argv[argc - 1]) == "--residuals") {

@@ -235,6 +235,17 @@ FLOW2D_API int flow2d_stage_solve_slab(flow2d_handle* h, const float* d_frame_0,
                             const float* d_flow_u, const float* d_flow_v, float* d_flow_du, float* d_flow_dv,
                             size_t w, size_t h_, float hx, float hy, const flow2d_params* p, int* slabbed);
 
+/* The same for callers that drive all GPUs from ONE process (the command line: cuda-flow2d --slab): N handles on the
+ * listed devices, wired mailbox to mailbox with peer access, one host thread per rank inside flow2d_slab_group_compute.
+ * Host images in (dense width*height floats, uploaded to every GPU), host flow out (every rank downloads its own rows);
+ * blocks until the flow is complete.  *device_ms (optional): slowest rank, first upload to last download. */
+typedef struct flow2d_slab_group flow2d_slab_group;
+FLOW2D_API int flow2d_slab_group_create(flow2d_slab_group** out, const int* devices, int n, size_t width, size_t height, int constancy);
+FLOW2D_API int flow2d_slab_group_compute(flow2d_slab_group* g, const float* frame_0, const float* frame_1, float* flow_u,
+                              float* flow_v, const flow2d_params* p, float* device_ms);
+FLOW2D_API int flow2d_slab_group_destroy(flow2d_slab_group* g);
+FLOW2D_API const char* flow2d_slab_group_last_error(const flow2d_slab_group* g);
+
 /* Debug aid, not part of the drop-in surface: every solve_pass CTA writes 8 %globaltimer stamps
  * (entry, loads+tensor, phi, weights, sweeps, stores) into d_stamps (device memory, >= 8 * CTAs of the
  * largest launch); NULL switches it off. */

@@ -241,3 +241,22 @@ def test_sequence_on_several_devices(synth, oracle, tmp_path):
         v = np.fromfile(tmp_path / "out" / ("%04d_flow-v-%d-%d.raw" % (i, w, h)), np.float32).reshape(h, w)
         ou, ov = oracle.compute_flow(frames[i], frames[i + 1], p)
         assert np.all(u == ou) and np.all(v == ov), "pair %d" % i
+
+
+def test_slab_mode_command_line(synth, tmp_path):
+    """cuda-flow2d --slab: one frame pair on several GPUs (the same device twice on a one-GPU box: two ranks, real
+    mailboxes and flags), output files byte-identical to the single-GPU command line."""
+    import torch
+    w, h = 160, 720
+    f0, f1, _, _ = synth.make_pair(w, h, 9, U0=(0.5, -0.3), U1=0.8, L=64.0)
+    f0.tofile(tmp_path / "a.raw")
+    f1.tofile(tmp_path / "b.raw")
+    (tmp_path / "one").mkdir()
+    (tmp_path / "two").mkdir()
+    r = _run(CLI, ["a.raw", "b.raw", w, h, "one/"], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    devs = "0-1" if torch.cuda.device_count() > 1 else "0,0"
+    r = _run(CLI, ["--slab", devs, "a.raw", "b.raw", w, h, "two/"], tmp_path)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    for name in ("flow-u-%d-%d.raw" % (w, h), "flow-v-%d-%d.raw" % (w, h), "res.pgm", "amp-%d-%d.raw" % (w, h)):
+        assert (tmp_path / "one" / name).read_bytes() == (tmp_path / "two" / name).read_bytes(), name
