@@ -9,7 +9,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 GREY, GRADIENT = 0, 1
-KERNEL_KINDS = 12  # FLOW2D_KERNEL_KINDS
+KERNEL_KINDS = 13  # FLOW2D_KERNEL_KINDS
+JACOBI, RED_BLACK = 0, 1  # FLOW2D_SCHEME_*
+TERM_DEFAULT, TERM_GRADIENT, TERM_LOG_GRADIENT, TERM_COMBINED = 0, 1, 2, 3  # FLOW2D_TERM_*
 MAX_LEVELS = 256   # FLOW2D_MAX_LEVELS
 
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
@@ -37,6 +39,14 @@ class Params(C.Structure):
         ("resident_levels", C.c_int),
         ("throughput_mode", C.c_int),
         ("report_residuals", C.c_int),
+        # opt-in extensions beyond the reference (all zero = reference behaviour)
+        ("scheme", C.c_int),
+        ("omega", C.c_float),
+        ("data_term", C.c_int),
+        ("gamma", C.c_float),
+        ("residual_tolerance", C.c_float),
+        ("residual_check_every", C.c_int),
+        ("cascaded_restriction", C.c_int),
     ]
 
 
@@ -81,6 +91,7 @@ def lib():
         L.flow2d_graph_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         dp = C.POINTER(C.c_double)
         L.flow2d_level_residuals.argtypes = [vp, dp, dp, C.c_int, C.POINTER(C.c_int)]
+        L.flow2d_level_outer_iterations.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
         L.flow2d_stage_residual.argtypes = [vp] + [vp] * 8 + [C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.POINTER(Params), dp, dp]
         L.flow2d_kernel_kind_name.argtypes = [C.c_int]
         L.flow2d_kernel_kind_name.restype = C.c_char_p
@@ -192,6 +203,12 @@ class Flow2D:
         ru, rv, n = (C.c_double * MAX_LEVELS)(), (C.c_double * MAX_LEVELS)(), C.c_int()
         self._check(lib().flow2d_level_residuals(self._h, ru, rv, MAX_LEVELS, C.byref(n)))
         return [(ru[i], rv[i]) for i in range(n.value)]
+
+    def level_outer_iterations(self):
+        """Outer iterations that ran per level of the last compute, coarsest level first (flow2d_level_outer_iterations)."""
+        it, n = (C.c_int * MAX_LEVELS)(), C.c_int()
+        self._check(lib().flow2d_level_outer_iterations(self._h, it, MAX_LEVELS, C.byref(n)))
+        return [int(it[i]) for i in range(n.value)]
 
     def stage_residual(self, d_f0, d_f1w, d_u, d_v, d_du, d_dv, d_phi, d_ksi, w, h, hx, hy, params):
         ru, rv = C.c_double(), C.c_double()

@@ -61,11 +61,12 @@ struct flow2d_handle {
   // a caller that rotates a few frame / flow containers (a frame ring, several pairs per handle) replays
   struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
-    unsigned char key[128] = {};
+    unsigned char key[192] = {};
     long long launches = 0;
     long long kind_launches[FLOW2D_KERNEL_KINDS] = {};
     int levels = 0, residual_levels = 0;
     int residual_px[FLOW2D_MAX_LEVELS] = {};
+    int iter_levels = 0, iter_default = 0;
     unsigned long long last_use = 0;
   };
   static constexpr int kGraphSlots = 8;
@@ -73,6 +74,15 @@ struct flow2d_handle {
   unsigned long long graph_clock = 0;
   long long graph_captures = 0, graph_replays = 0;
   int sm_count = 148;
+  // opt-in extensions (flow2d_params.scheme / omega / data_term / residual_tolerance / cascaded_restriction); allocated on first use
+  float* ext_pool = nullptr;      // six tensor planes of the extension data terms
+  float* J6[6] = {};
+  float* pyr_pool = nullptr;      // cascaded restriction: levels 1.. of both frame pyramids, row after row at the handle's pitch
+  size_t pyr_rows = 0;            // rows per frame the pool holds
+  int* d_stop = nullptr;          // FLOW2D_MAX_LEVELS stop words, then FLOW2D_MAX_LEVELS iteration counts
+  double* d_partials = nullptr;   // per-CTA partial sums of the convergence test
+  unsigned* d_counter = nullptr;
+  int iter_levels = 0, iter_default = 0;  // levels of the last compute / their outer iteration count when not stopped early
   // row-slab decomposition (flow2d_slab_connect): this handle is rank `slab_rank` of `slab_world`
   int slab_rank = 0, slab_world = 1;
   size_t slab_min_rows = 64;
@@ -111,7 +121,7 @@ int fail(flow2d_handle* h, int code, const char* fmt, ...) {
 
 const char* const kKindNames[FLOW2D_KERNEL_KINDS] = {"blur", "resample", "warp", "derivatives", "grad_tensor", "solve_pass",
                                                       "solve_pass(resident)", "solve_small_pass", "solve_tiny", "add_median",
-                                                      "add", "residual"};
+                                                      "add", "residual", "solve_ext"};
 
 int check_launch(flow2d_handle* h, int kind, int kernels) {
   cudaError_t e = cudaGetLastError();
@@ -317,13 +327,146 @@ int slab_exchange(flow2d_handle* h, float* fa, float* fb, const LevelGeom& g, in
   return FLOW2D_OK;
 }
 
+// ---- opt-in extensions --------------------------------------------------------------------------------------------
+// the relaxation itself differs from the reference's (another ordering, a relaxation factor, a tensor data term):
+// such levels are solved by the kernels of solve_ext.cu
+bool ext_solver(const flow2d_params* p) {
+  return p->scheme != FLOW2D_SCHEME_JACOBI || (p->omega != 0.f && p->omega != 1.f) || p->data_term != FLOW2D_TERM_DEFAULT;
+}
+bool early_exit(const flow2d_params* p) { return p->residual_tolerance > 0.f; }
+bool any_extension(const flow2d_params* p) { return ext_solver(p) || early_exit(p) || p->cascaded_restriction != 0; }
+
+void invalidate_graphs(flow2d_handle* h) {
+  for (auto& g : h->graphs)
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+}
+
+// rows of levels 1 .. levels-1 of one frame pyramid
+size_t pyramid_rows(const flow2d_handle* h, const flow2d_params* p, int levels, size_t* row_of /* [levels] or null */) {
+  size_t rows = 0;
+  for (int l = 1; l < levels; l++) {
+    size_t cw, ch; float hx, hy;
+    flow2d_level_geometry(h->W, h->H, p->warp_scale_factor, l, &cw, &ch, &hx, &hy);
+    if (row_of) row_of[l] = rows;
+    rows += ch;
+  }
+  return rows;
+}
+int levels_of(const flow2d_handle* h, const flow2d_params* p) {
+  const size_t max_level = flow2d_max_warp_level(h->W, h->H, p->warp_scale_factor);
+  return (int)(p->warp_levels_count < max_level ? p->warp_levels_count : max_level);
+}
+
+// Device memory of the extensions; must run OUTSIDE a stream capture (compute_on_device calls it first).
+int ensure_ext(flow2d_handle* h, const flow2d_params* p) {
+  if (ext_solver(p) && !h->ext_pool) {
+    const size_t csize = h->pitch * h->H;
+    if (cudaMalloc(&h->ext_pool, csize * 6 * sizeof(float)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(h, FLOW2D_ERR_OUT_OF_MEMORY, "allocation of the tensor planes failed");
+    }
+    CU_TRY(h, cudaMemset(h->ext_pool, 0, csize * 6 * sizeof(float)));
+    for (int k = 0; k < 6; k++) h->J6[k] = h->ext_pool + csize * k;
+  }
+  if (early_exit(p) && !h->d_stop) {
+    const size_t ctas = ((h->W + 31) / 32) * ((h->H + 7) / 8);
+    if (cudaMalloc(&h->d_stop, sizeof(int) * 2 * FLOW2D_MAX_LEVELS) != cudaSuccess ||
+        cudaMalloc(&h->d_partials, sizeof(double) * 2 * ctas) != cudaSuccess ||
+        cudaMalloc(&h->d_counter, sizeof(unsigned)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(h, FLOW2D_ERR_OUT_OF_MEMORY, "allocation of the convergence-test buffers failed");
+    }
+    CU_TRY(h, cudaMemset(h->d_stop, 0, sizeof(int) * 2 * FLOW2D_MAX_LEVELS));
+    CU_TRY(h, cudaMemset(h->d_counter, 0, sizeof(unsigned)));
+  }
+  if (p->cascaded_restriction) {
+    const size_t rows = pyramid_rows(h, p, levels_of(h, p), nullptr);
+    if (rows > h->pyr_rows) {
+      CU_TRY(h, cudaStreamSynchronize(h->stream));
+      invalidate_graphs(h);  // captured schedules point into the old pool
+      if (h->pyr_pool) cudaFree(h->pyr_pool);
+      h->pyr_pool = nullptr; h->pyr_rows = 0;
+      if (cudaMalloc(&h->pyr_pool, rows * h->pitch * 2 * sizeof(float)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(h, FLOW2D_ERR_OUT_OF_MEMORY, "allocation of the frame pyramids failed");
+      }
+      CU_TRY(h, cudaMemset(h->pyr_pool, 0, rows * h->pitch * 2 * sizeof(float)));
+      h->pyr_rows = rows;
+    }
+  }
+  return FLOW2D_OK;
+}
+
+// The convergence test after outer iteration `outer_done` (1-based) of level slot `slot`: sets the level's stop word
+// when both RMS residuals are <= residual_tolerance.  `which`: 1 = the increment is in the result pair, 2 = scratch pair.
+int enqueue_decide(flow2d_handle* h, const LevelGeom& g, const float* const* J, bool grad, const float* u, const float* v,
+                   const float* du, const float* dv, const float* phi, const float* ksi, const flow2d_params* p, int slot,
+                   int which, int outer_done) {
+  ResidualDecide d;
+  d.partials = h->d_partials; d.counter = h->d_counter; d.sums = nullptr;
+  d.stop = h->d_stop + slot; d.iterations = h->d_stop + FLOW2D_MAX_LEVELS + slot;
+  d.tol = p->residual_tolerance; d.which = which; d.outer_done = outer_done;
+  launch_residual_decide(h->stream, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, grad, u, v, du, dv, phi, ksi, g, p->equation_alpha, d);
+  return check_launch(h, FLOW2D_K_RESIDUAL, 1);
+}
+
+// The solve of one level with the kernels of solve_ext.cu (see there): tensor planes in
+// h->J6, one launch per sweep (red-black: per colour).  Result in du_a/dv_a.
+int run_solve_ext(flow2d_handle* h, const LevelGeom& g, const float* u, const float* v, float* du_a, float* dv_a, float* du_b,
+                  float* dv_b, float* phi, float* ksi, const flow2d_params* p, int slot) {
+  const int outer = (int)p->outer_iterations_count, inner = (int)p->inner_iterations_count;
+  cudaStream_t st = h->stream;
+  CU_TRY(h, cudaMemset2DAsync(du_a, h->pitch * 4, 0, (size_t)g.w * 4, g.h, st));
+  CU_TRY(h, cudaMemset2DAsync(dv_a, h->pitch * 4, 0, (size_t)g.w * 4, g.h, st));
+  if (outer == 0 || inner == 0) return FLOW2D_OK;
+  const bool rb = p->scheme == FLOW2D_SCHEME_RED_BLACK, early = early_exit(p);
+  const float omega = p->omega == 0.f ? 1.f : p->omega;
+  const int every = p->residual_check_every > 0 ? p->residual_check_every : 1;
+  const int* stop = early ? h->d_stop + slot : nullptr;
+  ExtTensor J;
+  for (int k = 0; k < 6; k++) J.p[k] = h->J6[k];
+  // Jacobi alternates between the two pairs: start where the last sweep ends in du_a/dv_a
+  float *cu = du_a, *cv = dv_a, *ou = du_b, *ov = dv_b;
+  if (!rb && (((long long)outer * inner) & 1)) {
+    CU_TRY(h, cudaMemset2DAsync(du_b, h->pitch * 4, 0, (size_t)g.w * 4, g.h, st));
+    CU_TRY(h, cudaMemset2DAsync(dv_b, h->pitch * 4, 0, (size_t)g.w * 4, g.h, st));
+    std::swap(cu, ou); std::swap(cv, ov);
+  }
+  for (int o = 0; o < outer; ++o) {
+    launch_ext_phi_ksi(st, J, u, v, cu, cv, phi, ksi, g, p->equation_smoothness, p->equation_data, stop);
+    TRY(check_launch(h, FLOW2D_K_EXT, 1));
+    for (int j = 0; j < inner; ++j) {
+      if (rb) {
+        launch_ext_sweep(st, J, u, v, cu, cv, phi, ksi, cu, cv, g, p->equation_alpha, omega, 0, stop);
+        launch_ext_sweep(st, J, u, v, cu, cv, phi, ksi, cu, cv, g, p->equation_alpha, omega, 1, stop);
+        TRY(check_launch(h, FLOW2D_K_EXT, 2));
+      } else {
+        launch_ext_sweep(st, J, u, v, cu, cv, phi, ksi, ou, ov, g, p->equation_alpha, omega, -1, stop);
+        TRY(check_launch(h, FLOW2D_K_EXT, 1));
+        std::swap(cu, ou); std::swap(cv, ov);
+      }
+    }
+    if (early && (o + 1) % every == 0)
+      TRY(enqueue_decide(h, g, h->J6, true, u, v, cu, cv, phi, ksi, p, slot, cu == du_a ? 1 : 2, o + 1));
+  }
+  if (early) {
+    launch_ext_pick(st, stop, du_b, dv_b, du_a, dv_a, g);
+    TRY(check_launch(h, FLOW2D_K_EXT, 1));
+  }
+  return FLOW2D_OK;
+}
+
 // CudaOperationSolve2D::Execute (cuda_operation_solve_2d.cpp:229-299) on top of the solve kernels.
 // The result is left in du_a/dv_a; du_b/dv_b are scratch.  fx,fy,ft (and J in gradient mode) must
 // hold the derivative planes of this level (on the own rows +- plan.in_margin when the level is slabbed).
 int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float* v, float* du_a, float* dv_a,
               float* du_b, float* dv_b, float* phi, float* ksi, bool want_phi, const flow2d_params* p,
-              const SolvePlan& pl) {
+              const SolvePlan& pl, int slot = 0) {
   const int outer = (int)p->outer_iterations_count, inner = (int)p->inner_iterations_count;
+  // convergence test (flow2d_params.residual_tolerance): every pass reads the level's stop word first; the levels that
+  // would run inside one CTA (solve_tiny, resident) go through the pass kernels so that the test sees every iteration
+  const bool early = early_exit(p) && !pl.slabbed;
+  const int every = p->residual_check_every > 0 ? p->residual_check_every : 1;
   if (outer == 0 || inner == 0) {
     // no sweep runs: the increment stays at its initial zero (cuda_operation_solve_2d.cpp:229-232)
     CU_TRY(h, cudaMemset2DAsync(du_a, h->pitch * 4, 0, (size_t)g.w * 4, g.h, h->stream));
@@ -347,10 +490,11 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   // the branch-free sqrt / rcp of the one-pixel kernels cover: take their plain IEEE variant from the start instead of
   // computing every outer iteration twice
   a.exact = (a.e_smooth * a.e_smooth < 0x1p-100f || a.e_data * a.e_data < 0x1p-100f) ? 1 : 0;
+  a.stop = early ? h->d_stop + slot : nullptr;
   const bool slabbed = pl.slabbed;
 
   // tiny levels (<= 1024 pixels): one CTA, one thread per pixel, all outer iterations in the kernel
-  if (!slabbed && p->resident_levels >= 0 && p->resident_levels != 2 && solve_tiny_fits(g.w, g.h)) {
+  if (!slabbed && !early && p->resident_levels >= 0 && p->resident_levels != 2 && solve_tiny_fits(g.w, g.h)) {
     a.du_in = a.dv_in = nullptr;
     a.phi_in = a.ksi_in = nullptr;
     a.du_out = du_a; a.dv_out = dv_a;
@@ -368,7 +512,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   const bool small_pass_instead = p->resident_levels == 0 && !p->throughput_mode && outer > 1 &&
                                   (p->sweeps_per_pass == 0 || p->sweeps_per_pass >= inner) &&
                                   inner <= FLOW2D_MAX_SWEEPS_PER_PASS && kSmallTS - 2 * (inner + 1) >= 4;
-  if (!slabbed && fits && p->resident_levels >= 0 && !small_pass_instead) {
+  if (!slabbed && !early && fits && p->resident_levels >= 0 && !small_pass_instead) {
     a.du_in = a.dv_in = nullptr;
     a.phi_in = a.ksi_in = nullptr;
     a.du_out = du_a; a.dv_out = dv_a;
@@ -427,7 +571,8 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       a.du_out = bufs[dst][0]; a.dv_out = bufs[dst][1];
       const bool first = (q == 0);
       a.phi_in = first ? nullptr : phi; a.ksi_in = first ? nullptr : ksi;
-      const bool store_phi = first && (npass > 1 || (want_phi && o == outer - 1));
+      const bool check = early && (o + 1) % every == 0;  // the convergence test needs this iteration's phi, ksi
+      const bool store_phi = first && (npass > 1 || (want_phi && o == outer - 1) || check);
       a.phi_out = store_phi ? phi : nullptr; a.ksi_out = store_phi ? ksi : nullptr;
       a.sweeps = s;
       a.halo_y = s + 1;
@@ -477,9 +622,23 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       }
       cur_du = a.du_out; cur_dv = a.dv_out;
     }
+    if (early && (o + 1) % every == 0) {
+      const float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
+      TRY(enqueue_decide(h, g, J, grad, u, v, cur_du, cur_dv, phi, ksi, p, slot, cur_du == du_a ? 1 : 2, o + 1));
+      after_exchange = true;  // the next pass follows the test kernel: no programmatic dependent launch
+    }
+  }
+  if (early) {
+    launch_ext_pick(h->stream, h->d_stop + slot, du_b, dv_b, du_a, dv_a, g);
+    TRY(check_launch(h, FLOW2D_K_EXT, 1));
   }
   return FLOW2D_OK;
 }
+
+// Derivative planes (and, for the extension data terms, the tensor planes) of a level, then its solve.
+int run_level_solve(flow2d_handle* h, const LevelGeom& g, const float* f0, const float* f1w, const float* u, const float* v,
+                    float* du_a, float* dv_a, float* du_b, float* dv_b, float* phi, float* ksi, bool want_phi,
+                    const flow2d_params* p, const SolvePlan& pl, int slot, int D0, int D1);
 
 // y0, y1: rows on which the solve needs fx, fy, ft (y1 <= y0: the whole level).  Gradient constancy takes central
 // differences of them (inside the reference's 16x8 tiles), so the derivative planes cover one row more on each side.
@@ -498,6 +657,30 @@ int run_derivatives(flow2d_handle* h, const LevelGeom& g, const float* f0, const
   return FLOW2D_OK;
 }
 
+int run_level_solve(flow2d_handle* h, const LevelGeom& g, const float* f0, const float* f1w, const float* u, const float* v,
+                    float* du_a, float* dv_a, float* du_b, float* dv_b, float* phi, float* ksi, bool want_phi,
+                    const flow2d_params* p, const SolvePlan& pl, int slot, int D0, int D1) {
+  if (!ext_solver(p)) {
+    TRY(run_derivatives(h, g, f0, f1w, D0, D1));
+    return run_solve(h, g, u, v, du_a, dv_a, du_b, dv_b, phi, ksi, want_phi, p, pl, slot);
+  }
+  // extension data terms: fx, fy, ft of the frames (or of log(1 + frame); the resampler's scratch planes are free at
+  // this point of a level), then the six tensor planes
+  if (p->data_term == FLOW2D_TERM_LOG_GRADIENT) {
+    launch_ext_log(h->stream, f0, h->c[C_TMP0], g);
+    launch_ext_log(h->stream, f1w, h->c[C_TMP1], g);
+    TRY(check_launch(h, FLOW2D_K_EXT, 2));
+    f0 = h->c[C_TMP0]; f1w = h->c[C_TMP1];
+  }
+  launch_derivatives(h->stream, f0, f1w, h->c[C_FX], h->c[C_FY], h->c[C_FT], g);
+  TRY(check_launch(h, FLOW2D_K_DERIVATIVES, 1));
+  ExtTensor J;
+  for (int k = 0; k < 6; k++) J.p[k] = h->J6[k];
+  launch_ext_tensor(h->stream, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, g, p->data_term, p->gamma);
+  TRY(check_launch(h, FLOW2D_K_EXT, 1));
+  return run_solve_ext(h, g, u, v, du_a, dv_a, du_b, dv_b, phi, ksi, p, slot);
+}
+
 int validate_params(flow2d_handle* h, const flow2d_params* p, int* median) {
   if (!p) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "params is null");
   if (!(p->warp_scale_factor > 0.f) || !(p->warp_scale_factor < 1.f))
@@ -510,6 +693,17 @@ int validate_params(flow2d_handle* h, const flow2d_params* p, int* median) {
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "sweeps_per_pass must be 0..%d", FLOW2D_MAX_SWEEPS_PER_PASS);
   if (p->outer_iterations_count > 1000000 || p->inner_iterations_count > 1000000)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "iteration counts out of range");
+  // opt-in extensions
+  if (p->scheme != FLOW2D_SCHEME_JACOBI && p->scheme != FLOW2D_SCHEME_RED_BLACK)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "scheme must be FLOW2D_SCHEME_JACOBI or FLOW2D_SCHEME_RED_BLACK");
+  if (!(p->omega >= 0.f) || !(p->omega < 2.f)) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "omega %g must be in [0, 2)", (double)p->omega);
+  if (p->data_term < FLOW2D_TERM_DEFAULT || p->data_term > FLOW2D_TERM_COMBINED)
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "data_term must be one of FLOW2D_TERM_*");
+  if (!(p->gamma >= 0.f) || !(p->gamma < 1e30f)) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "gamma must be finite and >= 0");
+  if (!(p->residual_tolerance >= 0.f)) return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "residual_tolerance must be >= 0");
+  if (h && ext_solver(p) && h->constancy != FLOW2D_GREY)
+    return fail(h, FLOW2D_ERR_UNSUPPORTED, "scheme / omega / data_term need a FLOW2D_GREY handle (use data_term = FLOW2D_TERM_GRADIENT "
+                                            "for gradient constancy)");
   return normalise_median(h, p->median_radius, median);
 }
 
@@ -524,7 +718,17 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
   cudaStream_t st = h->stream;
   h->levels_run = 0;
   const bool slab_on = slab && h->slab_world > 1;
+  if (slab_on && any_extension(p))
+    return fail(h, FLOW2D_ERR_UNSUPPORTED, "the opt-in extensions (scheme, omega, data_term, residual_tolerance, cascaded_restriction) "
+                                            "are not available in row-slab mode");
+  if (!slab_on && any_extension(p) &&
+      ((ext_solver(p) && !h->ext_pool) || (early_exit(p) && !h->d_stop) ||
+       (p->cascaded_restriction && h->pyr_rows < pyramid_rows(h, p, levels_of(h, p), nullptr))))
+    return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "internal: extension buffers not allocated");
   const bool residuals = p->report_residuals != 0 && !slab_on;
+  if (early_exit(p)) CU_TRY(h, cudaMemsetAsync(h->d_stop, 0, sizeof(int) * 2 * FLOW2D_MAX_LEVELS, st));
+  h->iter_levels = 0;
+  h->iter_default = (int)p->outer_iterations_count;
   h->residual_levels = 0;
   h->slab_levels = 0;
   if (residuals) CU_TRY(h, cudaMemsetAsync(h->d_residuals, 0, sizeof(double) * 2 * FLOW2D_MAX_LEVELS, st));
@@ -547,6 +751,27 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
   size_t pw = 0, ph = 0;
   const int e = h->constancy == FLOW2D_GRADIENT ? 1 : 0;
   bool prev_slabbed = false;
+
+  // cascaded restriction (extension): both frame pyramids once, level l from level l-1; the reference -- and the
+  // default path below -- restricts every level from the full-resolution frames (optical_flow_2d.cpp:279-305)
+  size_t pyr_row_of[FLOW2D_MAX_LEVELS + 64] = {};
+  const bool cascade = p->cascaded_restriction != 0 && level >= 1 && level < FLOW2D_MAX_LEVELS + 63;
+  auto pyr_level = [&](int frame_i, int l) { return h->pyr_pool + ((size_t)frame_i * h->pyr_rows + pyr_row_of[l]) * h->pitch; };
+  if (cascade) {
+    pyramid_rows(h, p, level + 1, pyr_row_of);
+    size_t lw = W, lh = H;
+    const float* src[2] = {frame[0], frame[1]};
+    for (int l = 1; l <= level; l++) {
+      size_t cw, ch; float hx, hy;
+      flow2d_level_geometry(W, H, p->warp_scale_factor, l, &cw, &ch, &hx, &hy);
+      ResampleJob jb[2];
+      for (int i = 0; i < 2; i++) jb[i] = ResampleJob{src[i], h->c[C_TMP0 + i], pyr_level(i, l), (int)lw, (int)lh, (int)cw, (int)ch, 0, 0, 0, 0, 0};
+      launch_resample_batch(st, jb, 2, (int)h->pitch);
+      TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
+      for (int i = 0; i < 2; i++) src[i] = pyr_level(i, l);
+      lw = cw; lh = ch;
+    }
+  }
 
   while (level >= 0) {
     size_t cw, ch;
@@ -572,7 +797,9 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     const float* fr[2] = {frame[0], frame[1]};
     ResampleJob jobs[4];
     int njobs = 0;
-    if (level != 0) {
+    if (level != 0 && cascade) {
+      fr[0] = pyr_level(0, level); fr[1] = pyr_level(1, level);
+    } else if (level != 0) {
       // (frame 1 is needed wherever the flow may point: all rows; frame 0 on the rows that are warped / differentiated)
       jobs[njobs++] = ResampleJob{frame[0], h->c[C_TMP0], h->c[C_RES0], (int)W, (int)H, g.w, g.h, W0, W1, 0, 0, 0};
       jobs[njobs++] = ResampleJob{frame[1], h->c[C_TMP1], h->c[C_RES1], (int)W, (int)H, g.w, g.h, 0, 0, 0, 0, 0};
@@ -593,12 +820,16 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     // backward registration (344-363) and the level's derivative planes
     launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g, W0, W1);
     TRY(check_launch(h, FLOW2D_K_WARP, 1));
-    TRY(run_derivatives(h, g, fr[0], h->c[C_WARPED], D0, D1));
     // solve (366-406)
-    TRY(run_solve(h, g, u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI], h->c[C_KSI], residuals, p, pl));
+    const int slot = h->iter_levels < FLOW2D_MAX_LEVELS ? h->iter_levels : FLOW2D_MAX_LEVELS - 1;
+    TRY(run_level_solve(h, g, fr[0], h->c[C_WARPED], u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI],
+                        h->c[C_KSI], residuals, p, pl, slot, D0, D1));
+    if (h->iter_levels < FLOW2D_MAX_LEVELS) ++h->iter_levels;
     if (residuals && h->residual_levels < FLOW2D_MAX_LEVELS && p->outer_iterations_count > 0 && p->inner_iterations_count > 0) {
+      const bool ext = ext_solver(p);
       const float* J[5] = {h->c[C_J0], h->c[C_J1], h->c[C_J2], h->c[C_J3], h->c[C_J4]};
-      launch_residual(st, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, h->constancy == FLOW2D_GRADIENT, u, v, h->c[C_DU0],
+      if (ext) for (int k = 0; k < 5; k++) J[k] = h->J6[k];
+      launch_residual(st, h->c[C_FX], h->c[C_FY], h->c[C_FT], J, ext || h->constancy == FLOW2D_GRADIENT, u, v, h->c[C_DU0],
                       h->c[C_DV0], h->c[C_PHI], h->c[C_KSI], g, p->equation_alpha, h->d_residuals + 2 * h->residual_levels);
       TRY(check_launch(h, FLOW2D_K_RESIDUAL, 1));
       h->residual_px[h->residual_levels++] = g.w * g.h;
@@ -680,6 +911,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
     GaussTaps taps;
     TRY(gauss_taps(h, p->gaussian_sigma, &taps));
   }
+  TRY(ensure_ext(h, p));  // allocations of the opt-in extensions: never inside a stream capture
   static const bool no_graph = std::getenv("FLOW2D_NO_GRAPH") != nullptr;  // A/B switch for measurements
   if (no_graph) return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
 
@@ -695,8 +927,11 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   key.p.resident_levels = p->resident_levels;
   key.p.throughput_mode = p->throughput_mode;
   key.p.report_residuals = p->report_residuals;
+  key.p.scheme = p->scheme; key.p.omega = p->omega; key.p.data_term = p->data_term; key.p.gamma = p->gamma;
+  key.p.residual_tolerance = p->residual_tolerance; key.p.residual_check_every = p->residual_check_every;
+  key.p.cascaded_restriction = p->cascaded_restriction;
   key.timing = h->timing;
-  static_assert(sizeof(GraphKey) <= sizeof(h->graphs[0].key), "graph key storage too small");
+  static_assert(sizeof(GraphKey) <= sizeof(flow2d_handle::GraphEntry::key), "graph key storage too small");
   flow2d_handle::GraphEntry* slot = nullptr;
   for (auto& g : h->graphs)
     if (g.exec && std::memcmp(&key, g.key, sizeof key) == 0) slot = &g;
@@ -709,6 +944,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
     h->levels_run = slot->levels;
     h->residual_levels = slot->residual_levels;
     std::memcpy(h->residual_px, slot->residual_px, sizeof h->residual_px);
+    h->iter_levels = slot->iter_levels; h->iter_default = slot->iter_default;
     return FLOW2D_OK;
   }
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -747,6 +983,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   slot->levels = h->levels_run;
   slot->residual_levels = h->residual_levels;
   std::memcpy(slot->residual_px, h->residual_px, sizeof h->residual_px);
+  slot->iter_levels = h->iter_levels; slot->iter_default = h->iter_default;
   slot->last_use = ++h->graph_clock;
   ++h->graph_captures;
   CU_TRY(h, cudaGraphLaunch(slot->exec, h->stream));
@@ -795,6 +1032,13 @@ void flow2d_default_params(flow2d_params* p) {
   p->resident_levels = 0;
   p->throughput_mode = 0;
   p->report_residuals = 0;
+  p->scheme = FLOW2D_SCHEME_JACOBI;
+  p->omega = 0.f;
+  p->data_term = FLOW2D_TERM_DEFAULT;
+  p->gamma = 0.f;
+  p->residual_tolerance = 0.f;
+  p->residual_check_every = 0;
+  p->cascaded_restriction = 0;
 }
 
 size_t flow2d_max_warp_level(size_t width, size_t height, float scale_factor) {
@@ -890,6 +1134,11 @@ int flow2d_destroy(flow2d_handle* h) {
   if (h->slab_counter) cudaFree(h->slab_counter);
   if (h->pool) cudaFree(h->pool);
   if (h->d_residuals) cudaFree(h->d_residuals);
+  if (h->ext_pool) cudaFree(h->ext_pool);
+  if (h->pyr_pool) cudaFree(h->pyr_pool);
+  if (h->d_stop) cudaFree(h->d_stop);
+  if (h->d_partials) cudaFree(h->d_partials);
+  if (h->d_counter) cudaFree(h->d_counter);
   delete h;
   return FLOW2D_OK;
 }
@@ -932,6 +1181,19 @@ int flow2d_level_residuals(flow2d_handle* h, double* rms_u, double* rms_v, int c
     if (rms_u) rms_u[i] = std::sqrt(sums[2 * i] / h->residual_px[i]);
     if (rms_v) rms_v[i] = std::sqrt(sums[2 * i + 1] / h->residual_px[i]);
   }
+  return FLOW2D_OK;
+}
+
+int flow2d_level_outer_iterations(flow2d_handle* h, int* iterations, int capacity, int* levels) {
+  STAGE_PROLOGUE(h);
+  if (levels) *levels = h->iter_levels;
+  if (!iterations || capacity <= 0 || h->iter_levels == 0) return FLOW2D_OK;
+  int used[FLOW2D_MAX_LEVELS] = {};
+  if (h->d_stop) {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy(used, h->d_stop + FLOW2D_MAX_LEVELS, sizeof(int) * h->iter_levels, cudaMemcpyDeviceToHost));
+  }
+  for (int i = 0; i < h->iter_levels && i < capacity; i++) iterations[i] = used[i] > 0 ? used[i] : h->iter_default;
   return FLOW2D_OK;
 }
 
@@ -1092,6 +1354,13 @@ int flow2d_slab_connect(flow2d_handle* h, int rank, int world, void* mailbox_abo
   h->peer[1] = static_cast<unsigned char*>(mailbox_below);
   h->slab_epoch = 0;
   h->slab_exchanges = 0; h->slab_bytes_sent = 0;
+  if (world > 1) {
+    // a rank's stream spins on flags its neighbours set: no kernel may be loaded lazily (with a context
+    // synchronisation) once the ranks are in flight
+    preload_pyramid_kernels(); preload_median_kernels(); preload_solve_kernels(); preload_solve_pass2_kernels();
+    preload_slab_kernels();
+    (void)cudaGetLastError();
+  }
   return FLOW2D_OK;
 }
 
@@ -1292,11 +1561,20 @@ int flow2d_stage_solve(flow2d_handle* h, const float* d_frame_0, const float* d_
   if (p->sweeps_per_pass < 0 || p->sweeps_per_pass > FLOW2D_MAX_SWEEPS_PER_PASS)
     return fail(h, FLOW2D_ERR_INVALID_ARGUMENT, "sweeps_per_pass must be 0..%d", FLOW2D_MAX_SWEEPS_PER_PASS);
   TRY(check_level(h, w, hh));
+  int median = 1;
+  flow2d_params q = *p;
+  q.median_radius = 1; q.cascaded_restriction = 0;  // not used by this stage
+  if (!(q.warp_scale_factor > 0.f && q.warp_scale_factor < 1.f)) q.warp_scale_factor = 0.9f;
+  if (q.warp_levels_count < 1) q.warp_levels_count = 1;
+  TRY(validate_params(h, &q, &median));
+  TRY(ensure_ext(h, &q));
+  if (early_exit(&q)) CU_TRY(h, cudaMemsetAsync(h->d_stop, 0, sizeof(int) * 2 * FLOW2D_MAX_LEVELS, h->stream));
+  h->iter_levels = 1; h->iter_default = (int)q.outer_iterations_count;
   const LevelGeom g = geom(h, w, hh, hx, hy);
-  TRY(run_derivatives(h, g, d_frame_0, d_frame_1));
   const bool want_phi = d_phi != nullptr;
-  return run_solve(h, g, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1],
-                   want_phi ? d_phi : h->c[C_PHI], want_phi ? d_ksi : h->c[C_KSI], want_phi, p, plan_solve(h, g, p, 1, false));
+  return run_level_solve(h, g, d_frame_0, d_frame_1, d_flow_u, d_flow_v, d_flow_du, d_flow_dv, h->c[C_DU1], h->c[C_DV1],
+                         want_phi ? d_phi : h->c[C_PHI], want_phi ? d_ksi : h->c[C_KSI], want_phi, &q,
+                         plan_solve(h, g, &q, 1, false), 0, 0, 0);
 }
 
 int flow2d_stage_add(flow2d_handle* h, float* d_a, const float* d_b, size_t w, size_t hh) {

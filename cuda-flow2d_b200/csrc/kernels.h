@@ -1,6 +1,7 @@
 // kernels.h -- launch interface of the sm_100a kernels (internal; the public boundary is include/flow2d.h).
 #pragma once
 
+#include "../../include/flow2d.h"
 #include "common.cuh"
 
 namespace flow2d {
@@ -54,6 +55,7 @@ struct SolveArgs {
   int y0, y1;                     // rows of the level this launch produces (0, h unless the level is slabbed)
   unsigned long long* timing;     // debug: 8 globaltimer stamps per CTA (null = off)
   int exact;                      // one-pixel kernels: 1 = plain IEEE div / sqrt / rcp from the start (see one_px_outer)
+  const int* stop;                // early exit (flow2d_params.residual_tolerance): return at once when *stop != 0; null = off
   int pdl;                        // 1 = launched with programmatic stream serialization: the previous kernel on the
                                   // stream is the previous pass of this solve (it writes only du/dv/phi/ksi)
 };
@@ -104,11 +106,46 @@ struct SlabUnpack {
 void launch_slab_push(cudaStream_t st, const SlabPush& p);
 void launch_slab_unpack(cudaStream_t st, const SlabUnpack& p);
 
+// loads every kernel of a translation unit now instead of at its first launch (see pyramid.cu: preload_pyramid_kernels)
+void preload_pyramid_kernels();
+void preload_median_kernels();
+void preload_solve_kernels();
+void preload_solve_pass2_kernels();
+void preload_slab_kernels();
+
 // ---- residual.cu (opt-in diagnostics, not on the default path) ----
 struct ResidualJ { const float* p[5]; };
 // adds the sums of r_u^2 and r_v^2 over the level to sums[0], sums[1]
 void launch_residual(cudaStream_t st, const float* fx, const float* fy, const float* ft, const float* const* J, bool grad,
                      const float* u, const float* v, const float* du, const float* dv, const float* phi, const float* ksi,
                      const LevelGeom& g, float alpha, double* sums);
+
+// the convergence test of flow2d_params.residual_tolerance (see residual.cu)
+struct ResidualDecide {
+  double* partials;      // 2 doubles per CTA of the launch
+  unsigned* counter;     // zero between launches
+  double* sums;          // optional: receives the two sums of squares (overwritten)
+  int* stop;             // the level's stop word
+  int* iterations;       // receives outer_done when the level stops
+  float tol;
+  int which, outer_done;
+};
+void launch_residual_decide(cudaStream_t st, const float* fx, const float* fy, const float* ft, const float* const* J, bool grad,
+                            const float* u, const float* v, const float* du, const float* dv, const float* phi, const float* ksi,
+                            const LevelGeom& g, float alpha, const ResidualDecide& d);
+
+// ---- solve_ext.cu (opt-in extensions: relaxation factor, red-black ordering, tensor data terms) ----
+struct ExtTensor { float* p[6]; };  // J11 J22 J12 J13 J23 J33
+void launch_ext_log(cudaStream_t st, const float* in, float* out, const LevelGeom& g);
+void launch_ext_tensor(cudaStream_t st, const float* fx, const float* fy, const float* ft, const ExtTensor& J, const LevelGeom& g,
+                       int term, float gamma);
+void launch_ext_phi_ksi(cudaStream_t st, const ExtTensor& J, const float* u, const float* v, const float* du, const float* dv,
+                        float* phi, float* ksi, const LevelGeom& g, float e_smooth, float e_data, const int* stop);
+// colour < 0: Jacobi (du_in -> du_out); 0 / 1: the cells of that colour in place (du_out == du_in)
+void launch_ext_sweep(cudaStream_t st, const ExtTensor& J, const float* u, const float* v, const float* du_in, const float* dv_in,
+                      const float* phi, const float* ksi, float* du_out, float* dv_out, const LevelGeom& g, float alpha,
+                      float omega, int colour, const int* stop);
+void launch_ext_pick(cudaStream_t st, const int* stop, const float* src_du, const float* src_dv, float* dst_du, float* dst_dv,
+                     const LevelGeom& g);
 
 }  // namespace flow2d

@@ -138,4 +138,13 @@ void launch_add(cudaStream_t st, float* a, const float* b, int w, int h, int pit
   add_kernel<<<grid, block, 0, st>>>(a, b, w, h, pitch);
 }
 
+void preload_median_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, add_median_kernel<1>);
+  cudaFuncGetAttributes(&a, add_median_kernel<3>);
+  cudaFuncGetAttributes(&a, add_median_kernel<5>);
+  cudaFuncGetAttributes(&a, add_median_kernel<7>);
+  cudaFuncGetAttributes(&a, add_kernel);
+}
+
 }  // namespace flow2d

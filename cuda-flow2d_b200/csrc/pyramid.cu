@@ -432,4 +432,18 @@ void launch_grad_tensor(cudaStream_t st, const float* fx, const float* fy, const
   grad_tensor_kernel<<<grid, block, 0, st>>>(fx, fy, ft, J[0], J[1], J[2], J[3], J[4], g.w, g.h, g.pitch, hx_1, hy_1, y0, y1);
 }
 
+// Lazy module loading (the CUDA 12 default) loads a kernel at its first launch and may synchronise the context to do so:
+// a rank whose stream spins on a neighbour's flag would then block the very launch it is waiting for when two ranks share
+// a device.  flow2d_slab_connect therefore loads every kernel up front.
+void preload_pyramid_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, blur_kernel);
+  cudaFuncGetAttributes(&a, resample_kernel<true>);
+  cudaFuncGetAttributes(&a, resample_kernel<false>);
+  cudaFuncGetAttributes(&a, resample_x_staged_kernel);
+  cudaFuncGetAttributes(&a, warp_kernel);
+  cudaFuncGetAttributes(&a, derivatives_kernel);
+  cudaFuncGetAttributes(&a, grad_tensor_kernel);
+}
+
 }  // namespace flow2d

@@ -14,15 +14,16 @@
 
 namespace flow2d {
 
+// r_u, r_v of one pixel (zero outside the level)
 template <bool GRAD>
-__global__ void __launch_bounds__(256)
-residual_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ ft, ResidualJ J,
-                const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ du,
-                const float* __restrict__ dv, const float* __restrict__ phi, const float* __restrict__ ksi, int w, int h,
-                int pitch, float hx_2, float hy_2, double* __restrict__ sums) {
+__device__ __forceinline__ void residual_px(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ ft,
+                                            const ResidualJ& J, const float* __restrict__ u, const float* __restrict__ v,
+                                            const float* __restrict__ du, const float* __restrict__ dv, const float* __restrict__ phi,
+                                            const float* __restrict__ ksi, int w, int h, int pitch, float hx_2, float hy_2,
+                                            double& ru, double& rv) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  double ru = 0.0, rv = 0.0;
+  ru = 0.0; rv = 0.0;
   if (x < w && y < h) {
     const int xm = mirror_clamp(x - 1, w), xp = mirror_clamp(x + 1, w);
     const int ym = mirror_clamp(y - 1, h), yp = mirror_clamp(y + 1, h);
@@ -50,7 +51,10 @@ residual_kernel(const float* __restrict__ fx, const float* __restrict__ fy, cons
     ru = k * (-J13 - J12 * d_v - J11 * d_u) + lap_u;
     rv = k * (-J23 - J12 * d_u - J22 * d_v) + lap_v;
   }
-  double a = ru * ru, b = rv * rv;
+}
+
+// sum of a, b over the CTA (32 x 8 threads); valid in thread (0, 0)
+__device__ __forceinline__ void cta_sum2(double& a, double& b) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -68,9 +72,69 @@ residual_kernel(const float* __restrict__ fx, const float* __restrict__ fy, cons
       a += __shfl_xor_sync(0xffffffffu, a, o);
       b += __shfl_xor_sync(0xffffffffu, b, o);
     }
-    if (lane == 0) {
-      atomicAdd(&sums[0], a);
-      atomicAdd(&sums[1], b);
+  }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(256)
+residual_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ ft, ResidualJ J,
+                const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ du,
+                const float* __restrict__ dv, const float* __restrict__ phi, const float* __restrict__ ksi, int w, int h,
+                int pitch, float hx_2, float hy_2, double* __restrict__ sums) {
+  double ru, rv;
+  residual_px<GRAD>(fx, fy, ft, J, u, v, du, dv, phi, ksi, w, h, pitch, hx_2, hy_2, ru, rv);
+  double a = ru * ru, b = rv * rv;
+  cta_sum2(a, b);
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    atomicAdd(&sums[0], a);
+    atomicAdd(&sums[1], b);
+  }
+}
+
+// The convergence test of flow2d_params.residual_tolerance: the same residual, summed in a FIXED order (per-CTA partial
+// sums, added up by the last CTA to finish) so that the decision does not depend on the order in which CTAs retire, then
+// compared on the device: when both RMS values are <= tol the level's stop word is set to `which` (1: the increment is in
+// the solver's result pair, 2: in its scratch pair) and every later kernel of the level returns at once.
+template <bool GRAD>
+__global__ void __launch_bounds__(256)
+residual_decide_kernel(const float* __restrict__ fx, const float* __restrict__ fy, const float* __restrict__ ft, ResidualJ J,
+                       const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ du,
+                       const float* __restrict__ dv, const float* __restrict__ phi, const float* __restrict__ ksi, int w, int h,
+                       int pitch, float hx_2, float hy_2, ResidualDecide d) {
+  if (*d.stop) return;
+  double ru, rv;
+  residual_px<GRAD>(fx, fy, ft, J, u, v, du, dv, phi, ksi, w, h, pitch, hx_2, hy_2, ru, rv);
+  double a = ru * ru, b = rv * rv;
+  cta_sum2(a, b);
+  const unsigned nblocks = gridDim.x * gridDim.y, me = blockIdx.y * gridDim.x + blockIdx.x;
+  __shared__ bool last;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    d.partials[2 * me] = a;
+    d.partials[2 * me + 1] = b;
+    __threadfence();
+    last = atomicAdd(d.counter, 1u) == nblocks - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // fixed order: thread t adds partials t, t + 256, ... ; then the fixed tree of cta_sum2
+  const unsigned t = threadIdx.y * blockDim.x + threadIdx.x;
+  a = 0.0; b = 0.0;
+  for (unsigned i = t; i < nblocks; i += 256) {
+    a += __ldcg(d.partials + 2 * i);
+    b += __ldcg(d.partials + 2 * i + 1);
+  }
+  __syncthreads();
+  cta_sum2(a, b);
+  if (t == 0) {
+    *d.counter = 0;
+    const double n = (double)w * (double)h;
+    const double rms_u = sqrt(a / n), rms_v = sqrt(b / n);
+    if (d.sums) { d.sums[0] = a; d.sums[1] = b; }
+    if (rms_u <= (double)d.tol && rms_v <= (double)d.tol) {
+      *d.iterations = d.outer_done;
+      __threadfence();
+      *d.stop = d.which;
     }
   }
 }
@@ -84,6 +148,17 @@ void launch_residual(cudaStream_t st, const float* fx, const float* fy, const fl
   dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
   if (grad) residual_kernel<true><<<grid, block, 0, st>>>(fx, fy, ft, j, u, v, du, dv, phi, ksi, g.w, g.h, g.pitch, hx_2, hy_2, sums);
   else residual_kernel<false><<<grid, block, 0, st>>>(fx, fy, ft, j, u, v, du, dv, phi, ksi, g.w, g.h, g.pitch, hx_2, hy_2, sums);
+}
+
+void launch_residual_decide(cudaStream_t st, const float* fx, const float* fy, const float* ft, const float* const* J, bool grad,
+                            const float* u, const float* v, const float* du, const float* dv, const float* phi, const float* ksi,
+                            const LevelGeom& g, float alpha, const ResidualDecide& d) {
+  ResidualJ j;
+  for (int i = 0; i < 5; i++) j.p[i] = J ? J[i] : nullptr;
+  const float hx_2 = alpha / (g.hx * g.hx), hy_2 = alpha / (g.hy * g.hy);
+  dim3 block(32, 8), grid((g.w + 31) / 32, (g.h + 7) / 8);
+  if (grad) residual_decide_kernel<true><<<grid, block, 0, st>>>(fx, fy, ft, j, u, v, du, dv, phi, ksi, g.w, g.h, g.pitch, hx_2, hy_2, d);
+  else residual_decide_kernel<false><<<grid, block, 0, st>>>(fx, fy, ft, j, u, v, du, dv, phi, ksi, g.w, g.h, g.pitch, hx_2, hy_2, d);
 }
 
 }  // namespace flow2d

@@ -106,4 +106,11 @@ void launch_slab_unpack(cudaStream_t st, const SlabUnpack& p) {
   slab_unpack_kernel<<<grid, block, 0, st>>>(p);
 }
 
+void preload_slab_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, slab_push_kernel);
+  cudaFuncGetAttributes(&a, slab_wait_kernel);
+  cudaFuncGetAttributes(&a, slab_unpack_kernel);
+}
+
 }  // namespace flow2d

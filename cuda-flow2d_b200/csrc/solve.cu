@@ -479,6 +479,7 @@ __device__ __forceinline__ void pass_body(const SolveArgs& a, float* sm) {
 template <bool GRAD, bool TIMING>
 __global__ void __launch_bounds__(NT, 1) solve_pass_kernel(const SolveArgs a) {
   extern __shared__ __align__(16) float sm[];
+  if (a.stop && *a.stop) return;  // the level has converged (flow2d_params.residual_tolerance)
   // does this CTA's region reach the image border (or beyond)?
   const int lx0 = blockIdx.x * a.ow - a.halo_x, ly0 = a.y0 + blockIdx.y * a.oh - a.halo_y;
   const bool border = lx0 <= 0 || lx0 + LW >= a.w || ly0 <= 0 || ly0 + (int)(blockDim.x >> 4) >= a.h;
@@ -751,6 +752,7 @@ template <bool GRAD, int TS>
 __global__ void __launch_bounds__(TS * TS, 1) solve_small_pass_kernel(const SolveArgs a) {
   constexpr int N = TS * TS;
   __shared__ __align__(16) float sq[kOnePxPlanes * N];
+  if (a.stop && *a.stop) return;  // the level has converged (flow2d_params.residual_tolerance)
   const int w = a.w, h = a.h;
   const int t = threadIdx.x, ly = t / TS, lx = t - ly * TS;
   const int ox0 = blockIdx.x * a.ow, oy0 = a.y0 + blockIdx.y * a.oh;
@@ -814,6 +816,20 @@ void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int
   if (ts == 16) launch_small_ts<16>(cfg, a, grad);
   else if (ts == 24) launch_small_ts<24>(cfg, a, grad);
   else launch_small_ts<32>(cfg, a, grad);
+}
+
+void preload_solve_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, solve_pass_kernel<false, false>);
+  cudaFuncGetAttributes(&a, solve_pass_kernel<true, false>);
+  cudaFuncGetAttributes(&a, solve_tiny_kernel<false>);
+  cudaFuncGetAttributes(&a, solve_tiny_kernel<true>);
+  cudaFuncGetAttributes(&a, solve_small_pass_kernel<false, 16>);
+  cudaFuncGetAttributes(&a, solve_small_pass_kernel<false, 24>);
+  cudaFuncGetAttributes(&a, solve_small_pass_kernel<false, 32>);
+  cudaFuncGetAttributes(&a, solve_small_pass_kernel<true, 16>);
+  cudaFuncGetAttributes(&a, solve_small_pass_kernel<true, 24>);
+  cudaFuncGetAttributes(&a, solve_small_pass_kernel<true, 32>);
 }
 
 }  // namespace flow2d

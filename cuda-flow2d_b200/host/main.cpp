@@ -18,6 +18,7 @@
 // files are also looked up under Input/Path@inputPath when they are not found in the CWD.
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <iostream>
 #include <string>
@@ -212,11 +213,32 @@ int main(int argc, char** argv) {
 
   if (argc >= 2 && string(argv[1]) == "--sequence") return run_sequence(argc, argv);
   if (argc >= 2 && string(argv[1]) == "--slab") return run_slab(argc, argv);
-  // optional trailing flag of the pair forms (not in the reference): per-level residual norms on stdout
-  bool report_residuals = false;
-  if (argc >= 2 && string(argv[argc - 1]) == "--residuals") {
-    report_residuals = true;
-    --argc;
+  // Optional flags of the pair forms (none of them exists upstream; without them the program behaves like the
+  // reference's): --residuals prints per-level residual norms; the rest switch on the opt-in solver extensions of
+  // include/flow2d.h (flow2d_params.scheme ... cascaded_restriction).  Flags may stand anywhere and are removed from argv.
+  bool report_residuals = false, cascaded = false;
+  int scheme = 0, data_term = 0, check_every = 0;
+  float omega = 0.f, gamma = 0.f, tolerance = 0.f;
+  {
+    int kept = 1;
+    for (int i = 1; i < argc; i++) {
+      const string a = argv[i];
+      auto val = [&](const char* key) -> const char* {
+        const size_t n = std::strlen(key);
+        return a.compare(0, n, key) == 0 ? a.c_str() + n : nullptr;
+      };
+      const char* v;
+      if (a == "--residuals") report_residuals = true;
+      else if (a == "--cascade") cascaded = true;
+      else if ((v = val("--scheme="))) scheme = (string(v) == "rb" || string(v) == "red-black") ? 1 : 0;
+      else if ((v = val("--omega="))) omega = (float)std::atof(v);
+      else if ((v = val("--term="))) data_term = string(v) == "gradient" ? 1 : string(v) == "log" ? 2 : string(v) == "combined" ? 3 : 0;
+      else if ((v = val("--gamma="))) gamma = (float)std::atof(v);
+      else if ((v = val("--tol="))) tolerance = (float)std::atof(v);
+      else if ((v = val("--check-every="))) check_every = std::atoi(v);
+      else argv[kept++] = argv[i];
+    }
+    argc = kept;
   }
 
   size_t width = 584, height = 388;
@@ -313,6 +335,13 @@ int main(int argc, char** argv) {
   params.PushValuePtr("median_radius", &median_radius);
   params.PushValuePtr("gaussian_sigma", &gaussian_sigma);
   if (report_residuals) params.PushValuePtr("report_residuals", &report_residuals);
+  if (scheme) params.PushValuePtr("solver_scheme", &scheme);
+  if (omega != 0.f) params.PushValuePtr("solver_omega", &omega);
+  if (data_term) params.PushValuePtr("data_term", &data_term);
+  if (gamma != 0.f) params.PushValuePtr("data_gamma", &gamma);
+  if (tolerance > 0.f) params.PushValuePtr("residual_tolerance", &tolerance);
+  if (check_every > 0) params.PushValuePtr("residual_check_every", &check_every);
+  if (cascaded) params.PushValuePtr("cascaded_restriction", &cascaded);
 
   flow_u.ZeroData();
   flow_v.ZeroData();

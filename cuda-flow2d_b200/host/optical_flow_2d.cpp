@@ -67,6 +67,14 @@ void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u
     return;
   // optional, beyond the reference's nine keys: "report_residuals" (bool*) prints the per-level residual norms
   if (void* opt = params.GetValuePtr("report_residuals")) p.report_residuals = *static_cast<bool*>(opt) ? 1 : 0;
+  // ... and the opt-in solver extensions of include/flow2d.h (absent keys = the reference's behaviour)
+  if (void* opt = params.GetValuePtr("solver_scheme")) p.scheme = *static_cast<int*>(opt);
+  if (void* opt = params.GetValuePtr("solver_omega")) p.omega = *static_cast<float*>(opt);
+  if (void* opt = params.GetValuePtr("data_term")) p.data_term = *static_cast<int*>(opt);
+  if (void* opt = params.GetValuePtr("data_gamma")) p.gamma = *static_cast<float*>(opt);
+  if (void* opt = params.GetValuePtr("residual_tolerance")) p.residual_tolerance = *static_cast<float*>(opt);
+  if (void* opt = params.GetValuePtr("residual_check_every")) p.residual_check_every = *static_cast<int*>(opt);
+  if (void* opt = params.GetValuePtr("cascaded_restriction")) p.cascaded_restriction = *static_cast<bool*>(opt) ? 1 : 0;
   for (Data2D* d : {&frame_0, &frame_1, &flow_u, &flow_v})
     if (d->Width() != size_.width || d->Height() != size_.height || !d->DataPtr()) {
       std::printf("Error: '%s': frames and flow fields must be %zux%zu.\n", GetName(), size_.width, size_.height);
@@ -83,6 +91,15 @@ void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u
   int levels = 0;
   flow2d_last_stats(handle_, &launches, &levels, &last_gpu_time_ms);
   if (!silent) std::printf("Levels: %d, kernel launches: %lld\n", levels, launches);
+  if (p.residual_tolerance > 0.f) {
+    int it[FLOW2D_MAX_LEVELS], n = 0;
+    if (flow2d_level_outer_iterations(handle_, it, FLOW2D_MAX_LEVELS, &n) == FLOW2D_OK) {
+      long long total = 0;
+      for (int i = 0; i < n; i++) total += it[i];
+      std::printf("Outer iterations run: %lld of %lld (convergence test at %g)\n", total, (long long)n * (long long)p.outer_iterations_count,
+                  (double)p.residual_tolerance);
+    }
+  }
   if (p.report_residuals) {
     double ru[FLOW2D_MAX_LEVELS], rv[FLOW2D_MAX_LEVELS];
     int n = 0;

@@ -73,7 +73,33 @@ typedef struct flow2d_params {
                                     for 4-8 handles sharing the GPU; 1 is kept for many handles on a saturated GPU */
   int    report_residuals;       /* opt-in diagnostics (no reference counterpart, see flow2d_level_residuals): 1 = record
                                     the residual norm of every level's last linear system; results are unchanged */
+  /* ---- opt-in EXTENSIONS beyond the reference.  All zero (flow2d_default_params) = the
+   * reference's behaviour, bit for bit.  Anything else changes the result BY DESIGN and is specified by, and tested
+   * against, oracle/flow2d_oracle_ext.c -- never against the reference, which has none of it:
+   * fixed Jacobi counts without a relaxation factor (solve_2d.cu:361-374, cuda_operation_solve_2d.cpp:229-299), every
+   * level restricted from the original frames (optical_flow_2d.cpp:279-305), derivative halos of the gradient / log
+   * terms taken from the CUDA block (solve_2d.cu:391-669, 813-841), README.md:32-34's two data terms never combined. */
+  int    scheme;                 /* FLOW2D_SCHEME_JACOBI (reference) or FLOW2D_SCHEME_RED_BLACK: Gauss-Seidel in red-black
+                                    order (cells with even x+y first), in place */
+  float  omega;                  /* relaxation factor: new = old + omega * (update - old); 0 or 1 = none.  With red-black
+                                    ordering this is SOR (1 < omega < 2) */
+  int    data_term;              /* FLOW2D_TERM_*: tensor data terms with true (mirrored) neighbour halos and the robust
+                                    weight on the full tensor; needs a FLOW2D_GREY handle */
+  float  gamma;                  /* FLOW2D_TERM_COMBINED: J = J_brightness + gamma * J_gradient */
+  float  residual_tolerance;     /* > 0: convergence test -- a level stops iterating once both RMS residuals of its lagged
+                                    system (see flow2d_level_residuals) are <= this; decided on the device, no host sync */
+  int    residual_check_every;   /* test after every n-th outer iteration (<= 0: every one) */
+  int    cascaded_restriction;   /* 1: level l of the two frame pyramids is restricted from level l-1 (once, before the
+                                    level loop) instead of from the full-resolution frame */
 } flow2d_params;
+
+enum { FLOW2D_SCHEME_JACOBI = 0, FLOW2D_SCHEME_RED_BLACK = 1 };
+enum {
+  FLOW2D_TERM_DEFAULT = 0,       /* the handle's flow2d_constancy, as the reference computes it */
+  FLOW2D_TERM_GRADIENT = 1,      /* gradient constancy, second derivatives over the true neighbours */
+  FLOW2D_TERM_LOG_GRADIENT = 2,  /* the same on log(1 + f): DataConstancy::LogDerivatives done right */
+  FLOW2D_TERM_COMBINED = 3       /* brightness + gamma * gradient constancy, jointly robustified */
+};
 
 #define FLOW2D_MAX_SWEEPS_PER_PASS 7
 #define FLOW2D_MAX_LEVELS 256    /* residuals are recorded for at most this many levels (the coarsest ones) */
@@ -125,6 +151,7 @@ enum {
   FLOW2D_K_BLUR = 0, FLOW2D_K_RESAMPLE, FLOW2D_K_WARP, FLOW2D_K_DERIVATIVES, FLOW2D_K_GRAD_TENSOR, FLOW2D_K_SOLVE_PASS,
   FLOW2D_K_SOLVE_RESIDENT, FLOW2D_K_SOLVE_SMALL_PASS, FLOW2D_K_SOLVE_TINY, FLOW2D_K_ADD_MEDIAN, FLOW2D_K_ADD,
   FLOW2D_K_RESIDUAL,
+  FLOW2D_K_EXT,  /* the kernels of the opt-in extensions (csrc/solve_ext.cu) */
   FLOW2D_KERNEL_KINDS
 };
 FLOW2D_API int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts /* [FLOW2D_KERNEL_KINDS] */);
@@ -150,6 +177,10 @@ FLOW2D_API int flow2d_stage_residual(flow2d_handle* h, const float* d_frame_0, c
                           const float* d_u, const float* d_v, const float* d_du, const float* d_dv,
                           const float* d_phi, const float* d_ksi, size_t w, size_t hh, float hx, float hy,
                           const flow2d_params* p, double* rms_u, double* rms_v);
+
+/* Outer iterations that ran per level in the last flow2d_compute*() call, coarsest level first (equal to
+ * outer_iterations_count unless residual_tolerance ended a level early).  Waits for the handle's stream. */
+FLOW2D_API int flow2d_level_outer_iterations(flow2d_handle* h, int* iterations, int capacity, int* levels);
 
 /* ---- level table: replaces OpticalFlowBase2D::GetMaxWarpLevel and the per-level size formulas ---
  * (src/optical_flow/optical_flow_base_2d.cpp:36-59, src/optical_flow/optical_flow_2d.cpp:268-272).

@@ -101,6 +101,36 @@ int oracle_median(const float* in, float* out, size_t w, size_t h, size_t pitch,
 int oracle_compute_flow(const float* f0, const float* f1, size_t W, size_t H,
                         const oracle_params* p, float* u, float* v);
 
+/* ---- EXTENSIONS beyond the reference (flow2d_oracle_ext.c): a specification for the opt-in features of SURVEY.md 8(f)
+ * ranks 3-4, never reference parity.  Checks flow2d_params.{scheme, omega, data_term, gamma, residual_tolerance,
+ * residual_check_every, cascaded_restriction}. */
+enum { ORACLE_SCHEME_JACOBI = 0, ORACLE_SCHEME_RED_BLACK = 1 };
+enum { ORACLE_TERM_DEFAULT = 0, ORACLE_TERM_GRADIENT = 1, ORACLE_TERM_LOG_GRADIENT = 2, ORACLE_TERM_COMBINED = 3 };
+typedef struct oracle_ext {
+  int   scheme;                /* ORACLE_SCHEME_* */
+  float omega;                 /* relaxation factor; 0 or 1 = none */
+  int   data_term;             /* ORACLE_TERM_* */
+  float gamma;                 /* weight of the gradient tensor in ORACLE_TERM_COMBINED */
+  float residual_tolerance;    /* > 0: a level ends when both RMS residuals are <= this */
+  int   residual_check_every;  /* test after every n-th outer iteration (<= 0: 1) */
+  int   cascaded_restriction;  /* 1: level l of the frame pyramid is restricted from level l-1 */
+} oracle_ext;
+void oracle_ext_tensor(const float* f0, const float* f1w, size_t w, size_t h, size_t pitch, float hx, float hy,
+                       int data_term, float gamma, float* const J[6]);
+void oracle_ext_phi_ksi(const float* const J[6], const float* u, const float* v, const float* du, const float* dv,
+                        size_t w, size_t h, size_t pitch, float hx, float hy, float e_smooth, float e_data, float* phi,
+                        float* ksi);
+void oracle_ext_residual(const float* const J[6], const float* u, const float* v, const float* du, const float* dv,
+                         const float* phi, const float* ksi, size_t w, size_t h, size_t pitch, float hx, float hy,
+                         float alpha, double* rms_u, double* rms_v);
+/* returns the outer iterations that ran; du, dv, phi, ksi are pitch*h caller buffers */
+int oracle_ext_solve_level(const float* f0, const float* f1w, const float* u, const float* v, float* du, float* dv,
+                           float* phi, float* ksi, size_t w, size_t h, size_t pitch, float hx, float hy,
+                           const oracle_params* p, const oracle_ext* e);
+/* returns the levels run; outer_used[cap] (optional): outer iterations per level, coarsest first */
+int oracle_ext_compute_flow(const float* f0, const float* f1, size_t W, size_t H, const oracle_params* p,
+                            const oracle_ext* e, float* u, float* v, int* outer_used, int cap);
+
 /* number of OpenMP threads the oracle will use (1 if built without OpenMP) */
 int oracle_num_threads(void);
 void oracle_set_num_threads(int n);

@@ -38,7 +38,8 @@ def make_params(levels=50, scale=0.9, outer=40, inner=5, alpha=35.0, e_smooth=0.
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "flow2d_oracle.c")):
+    srcs = [os.path.join(_HERE, f) for f in ("flow2d_oracle.c", "flow2d_oracle_ext.c", "flow2d_oracle.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -197,6 +198,70 @@ def compute_flow(f0, f1, params):
     if rc != 0:
         raise RuntimeError("oracle_compute_flow failed: %d" % rc)
     return u, v
+
+
+# ---- EXTENSIONS beyond the reference (flow2d_oracle_ext.c): the specification the opt-in features are checked against ----
+JACOBI, RED_BLACK = 0, 1
+TERM_DEFAULT, TERM_GRADIENT, TERM_LOG_GRADIENT, TERM_COMBINED = 0, 1, 2, 3
+
+
+class Ext(C.Structure):
+    """Mirror of `oracle_ext` (flow2d_oracle.h)."""
+    _fields_ = [
+        ("scheme", C.c_int),
+        ("omega", C.c_float),
+        ("data_term", C.c_int),
+        ("gamma", C.c_float),
+        ("residual_tolerance", C.c_float),
+        ("residual_check_every", C.c_int),
+        ("cascaded_restriction", C.c_int),
+    ]
+
+
+def make_ext(scheme=JACOBI, omega=1.0, data_term=TERM_DEFAULT, gamma=0.0, residual_tolerance=0.0, residual_check_every=1,
+             cascaded_restriction=0):
+    return Ext(scheme, omega, data_term, gamma, residual_tolerance, residual_check_every, cascaded_restriction)
+
+
+def ext_tensor(f0, f1w, hx, hy, data_term, gamma=0.0):
+    """Six tensor planes J11 J22 J12 J13 J23 J33 of a level."""
+    f0, f1w = _f32(f0), _f32(f1w)
+    h, w = f0.shape
+    J = [np.zeros_like(f0) for _ in range(6)]
+    arr = (C.POINTER(C.c_float) * 6)(*[_p(j) for j in J])
+    fn = lib().oracle_ext_tensor
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]
+    fn(_p(f0), _p(f1w), w, h, w, hx, hy, data_term, gamma, arr)
+    return J
+
+
+def ext_solve_level(f0, f1w, u, v, hx, hy, params, ext):
+    """One level with the extensions; returns (du, dv, phi, ksi, outer iterations that ran)."""
+    f0, f1w, u, v = map(_f32, (f0, f1w, u, v))
+    h, w = f0.shape
+    du, dv, phi, ksi = (np.zeros_like(f0) for _ in range(4))
+    fn = lib().oracle_ext_solve_level
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 8 + [C.c_size_t] * 3 + [C.c_float, C.c_float, C.POINTER(Params), C.POINTER(Ext)]
+    used = fn(_p(f0), _p(f1w), _p(u), _p(v), _p(du), _p(dv), _p(phi), _p(ksi), w, h, w, hx, hy, C.byref(params), C.byref(ext))
+    return du, dv, phi, ksi, int(used)
+
+
+def ext_compute_flow(f0, f1, params, ext):
+    """The whole path with the extensions; returns (u, v, [outer iterations per level, coarsest first])."""
+    f0, f1 = _f32(f0), _f32(f1)
+    h, w = f0.shape
+    u, v = np.empty_like(f0), np.empty_like(f0)
+    used = (C.c_int * 256)()
+    fn = lib().oracle_ext_compute_flow
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(Params), C.POINTER(Ext), C.c_void_p, C.c_void_p,
+                   C.c_void_p, C.c_int]
+    n = fn(_p(f0), _p(f1), w, h, C.byref(params), C.byref(ext), _p(u), _p(v), used, 256)
+    if n < 0:
+        raise RuntimeError("oracle_ext_compute_flow failed: %d" % n)
+    return u, v, [int(used[i]) for i in range(min(n, 256))]
 
 
 def num_threads():
