@@ -74,6 +74,7 @@ struct flow2d_handle {
   unsigned long long graph_clock = 0;
   long long graph_captures = 0, graph_replays = 0;
   int sm_count = 148;
+  bool pass3 = false;             // the TMA-staged persistent pass (solve_pass3.cu) is usable on this device / driver
   // opt-in extensions (flow2d_params.scheme / omega / data_term / residual_tolerance / cascaded_restriction); allocated on first use
   float* ext_pool = nullptr;      // six tensor planes of the extension data terms
   float* J6[6] = {};
@@ -615,9 +616,11 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
         }
       }
       if (!small) {
-        static const bool v1 = std::getenv("FLOW2D_SOLVE_V1") != nullptr;  // A/B switch: the first-generation tiled kernel
-        if (v1) launch_solve_pass(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
-        else launch_solve_pass2(h->stream, a, grad, (g.w + a.ow - 1) / a.ow, (vb - va + a.oh - 1) / a.oh);
+        static const bool v1 = std::getenv("FLOW2D_SOLVE_V1") != nullptr;  // A/B switches: the earlier generations of the tiled kernel
+        static const bool v2 = std::getenv("FLOW2D_SOLVE_V2") != nullptr;
+        const int tx = (g.w + a.ow - 1) / a.ow, ty = (vb - va + a.oh - 1) / a.oh;
+        if (v1) launch_solve_pass(h->stream, a, grad, tx, ty);
+        else if (grad || v2 || !h->pass3 || !launch_solve_pass3(h->stream, a, tx, ty, h->sm_count)) launch_solve_pass2(h->stream, a, grad, tx, ty);
         TRY(check_launch(h, FLOW2D_K_SOLVE_PASS, 1));
       }
       cur_du = a.du_out; cur_dv = a.dv_out;
@@ -1108,13 +1111,14 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
   }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
-      solve_pass_configure() != cudaSuccess || solve_pass2_configure() != cudaSuccess || cudaMemsetAsync(h->pool, 0, csize * ncont * sizeof(float), h->own_stream) != cudaSuccess ||
+      solve_pass_configure() != cudaSuccess || solve_pass2_configure() != cudaSuccess || solve_pass3_configure() != cudaSuccess || cudaMemsetAsync(h->pool, 0, csize * ncont * sizeof(float), h->own_stream) != cudaSuccess ||
       cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
     (void)cudaGetLastError();
     flow2d_destroy(h);
     return FLOW2D_ERR_CUDA;
   }
   h->stream = h->own_stream;
+  h->pass3 = solve_pass3_available();
   *out = h;
   return FLOW2D_OK;
 }
@@ -1357,7 +1361,7 @@ int flow2d_slab_connect(flow2d_handle* h, int rank, int world, void* mailbox_abo
   if (world > 1) {
     // a rank's stream spins on flags its neighbours set: no kernel may be loaded lazily (with a context
     // synchronisation) once the ranks are in flight
-    preload_pyramid_kernels(); preload_median_kernels(); preload_solve_kernels(); preload_solve_pass2_kernels();
+    preload_pyramid_kernels(); preload_median_kernels(); preload_solve_kernels(); preload_solve_pass2_kernels(); preload_solve_pass3_kernels();
     preload_slab_kernels();
     (void)cudaGetLastError();
   }

@@ -70,6 +70,14 @@ size_t solve_pass2_smem_bytes();
 cudaError_t solve_pass2_configure();
 void launch_solve_pass2(cudaStream_t st, const SolveArgs& a, bool grad, int grid_x, int grid_y);
 
+// third generation (solve_pass3.cu): persistent CTAs, input tiles by TMA (cp.async.bulk.tensor + mbarrier) prefetched during
+// the sweeps of the previous tile; brightness constancy only.  launch_solve_pass3 returns false when the tensor maps or the
+// launch could not be made (the caller then uses solve_pass2).  ctas: persistent CTAs to launch (the SM count).
+size_t solve_pass3_smem_bytes();
+cudaError_t solve_pass3_configure();
+bool solve_pass3_available();
+bool launch_solve_pass3(cudaStream_t st, const SolveArgs& a, int grid_x, int grid_y, int ctas);
+
 // one pass of a mid-size level with one thread per pixel: ts x ts regions (ts = 32, 24 or 16), a.halo_x = a.halo_y =
 // a.sweeps + 1, a.ow = a.oh = ts - 2 * halo; phi/ksi are always computed in the pass (a.phi_in must be null)
 constexpr int kSmallTS = 32;
@@ -111,6 +119,7 @@ void preload_pyramid_kernels();
 void preload_median_kernels();
 void preload_solve_kernels();
 void preload_solve_pass2_kernels();
+void preload_solve_pass3_kernels();
 void preload_slab_kernels();
 
 // ---- residual.cu (opt-in diagnostics, not on the default path) ----
