@@ -484,8 +484,13 @@ def kernel_detail(ctx, wl, key, fl, stream, d0, d1, ms_per_pair):
     alg_bytes = bpp * cw * ch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     unfused = (32.0 + 40.0 * sweeps) if bpp == 32.0 else 40.0 * sweeps
+    # the tiled pass has three generations (csrc/solve.cu, solve_pass2.cu, solve_pass3.cu); name the one that ran
+    gen = kname.replace("(resident)", "")
+    if kname == "solve_pass":
+        gen = ("solve_pass" if os.environ.get("FLOW2D_SOLVE_V1") else
+               "solve_pass2" if (wl.get("gradient") or os.environ.get("FLOW2D_SOLVE_V2")) else "solve_pass3")
     roof = {"kernel": "%s_kernel<%s> at the finest level it runs on (%dx%d; %d launches per solve, %.3g Jacobi sweeps per launch)" %
-                      (kname.replace("(resident)", ""), "gradient" if wl.get("gradient") else "grey", cw, ch, n_pass, sweeps),
+                      (gen, "gradient" if wl.get("gradient") else "grey", cw, ch, n_pass, sweeps),
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": ncu_traffic("solve_" + key), "peak_source": peak_src, "launch_us": launch_ms * 1e3,
             "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_pixel": bpp,

@@ -47,6 +47,7 @@ class Params(C.Structure):
         ("residual_tolerance", C.c_float),
         ("residual_check_every", C.c_int),
         ("cascaded_restriction", C.c_int),
+        ("report_level_times", C.c_int),
     ]
 
 
@@ -91,6 +92,7 @@ def lib():
         L.flow2d_graph_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         dp = C.POINTER(C.c_double)
         L.flow2d_level_residuals.argtypes = [vp, dp, dp, C.c_int, C.POINTER(C.c_int)]
+        L.flow2d_level_times.argtypes = [vp, fp, fp, C.c_int, C.POINTER(C.c_int)]
         L.flow2d_level_outer_iterations.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
         L.flow2d_stage_residual.argtypes = [vp] + [vp] * 8 + [C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.POINTER(Params), dp, dp]
         L.flow2d_kernel_kind_name.argtypes = [C.c_int]
@@ -203,6 +205,12 @@ class Flow2D:
         ru, rv, n = (C.c_double * MAX_LEVELS)(), (C.c_double * MAX_LEVELS)(), C.c_int()
         self._check(lib().flow2d_level_residuals(self._h, ru, rv, MAX_LEVELS, C.byref(n)))
         return [(ru[i], rv[i]) for i in range(n.value)]
+
+    def level_times(self):
+        """[(level_ms, solve_ms)] of the last compute with params.report_level_times = 1, coarsest level first."""
+        a, b, n = (C.c_float * MAX_LEVELS)(), (C.c_float * MAX_LEVELS)(), C.c_int()
+        self._check(lib().flow2d_level_times(self._h, a, b, MAX_LEVELS, C.byref(n)))
+        return [(a[i], b[i]) for i in range(n.value)]
 
     def level_outer_iterations(self):
         """Outer iterations that ran per level of the last compute, coarsest level first (flow2d_level_outer_iterations)."""

@@ -15,6 +15,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/flow2d.h"
 #include "kernels.h"
 
@@ -35,6 +37,7 @@ enum Container {
   C_FX, C_FY, C_FT,
   C_TMP0, C_TMP1,      // x-pass results of the resampler
   C_OUT_U, C_OUT_V,    // final flow of flow2d_compute (host API)
+  C_IN2, C_IN3,        // second set of uploaded frames: flow2d_compute_async uploads call n+1 while call n computes
   C_J0, C_J1, C_J2, C_J3, C_J4,  // gradient mode only
   C_COUNT
 };
@@ -47,6 +50,11 @@ struct flow2d_handle {
   int constancy = FLOW2D_GREY;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  // host API: the frames of a call are uploaded on a stream of their own into one of two input sets, so the upload of
+  // the next call overlaps the computation of the current one (a sequence through one handle, several handles per GPU)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+  unsigned long long async_calls = 0;
   float* pool = nullptr;
   float* c[C_COUNT] = {};
   long long launches = 0;
@@ -84,6 +92,9 @@ struct flow2d_handle {
   double* d_partials = nullptr;   // per-CTA partial sums of the convergence test
   unsigned* d_counter = nullptr;
   int iter_levels = 0, iter_default = 0;  // levels of the last compute / their outer iteration count when not stopped early
+  // per-level timers (flow2d_params.report_level_times): events at the start of a level, before and after its solve
+  std::vector<cudaEvent_t> level_events;
+  int timed_levels = 0;
   // row-slab decomposition (flow2d_slab_connect): this handle is rank `slab_rank` of `slab_world`
   int slab_rank = 0, slab_world = 1;
   size_t slab_min_rows = 64;
@@ -135,6 +146,16 @@ void reset_launch_counts(flow2d_handle* h) {
   h->launches = 0;
   for (auto& k : h->kind_launches) k = 0;
 }
+
+// NVTX ranges around what the host enqueues per stage and level (the reference has two event timers and
+// nothing else).  Header-only NVTX3: a no-op costing a few nanoseconds unless a profiler is attached.  Kernels of a
+// replayed CUDA graph carry no host range; run with FLOW2D_NO_GRAPH=1 under nsys / ncu --nvtx to see them per level.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 #define TRY(expr)              \
   do {                         \
@@ -736,9 +757,23 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
   h->slab_levels = 0;
   if (residuals) CU_TRY(h, cudaMemsetAsync(h->d_residuals, 0, sizeof(double) * 2 * FLOW2D_MAX_LEVELS, st));
 
+  const bool level_times = p->report_level_times != 0 && !slab_on;
+  h->timed_levels = 0;
+  auto stamp_level = [&](int slot) {  // event `slot` (0: level start, 1: solve start, 2: solve end) of the current level
+    if (!level_times || h->timed_levels >= FLOW2D_MAX_LEVELS) return;
+    const size_t i = (size_t)h->timed_levels * 3 + slot;
+    while (h->level_events.size() <= i) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return; }
+      h->level_events.push_back(e);
+    }
+    cudaEventRecord(h->level_events[i], st);
+  };
+
   // presmoothing (optical_flow_2d.cpp:218-246)
   const float* frame[2] = {frame_0, frame_1};
   if (p->gaussian_sigma > 0.0f) {
+    NvtxRange r_blur("flow2d: presmoothing");
     GaussTaps taps;
     TRY(gauss_taps(h, p->gaussian_sigma, &taps));
     for (int i = 0; i < 2; i++) {
@@ -781,6 +816,10 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     float hx, hy;
     flow2d_level_geometry(W, H, p->warp_scale_factor, level, &cw, &ch, &hx, &hy);
     const LevelGeom g = geom(h, cw, ch, hx, hy);
+    char range_name[64];
+    std::snprintf(range_name, sizeof range_name, "flow2d: level %d (%zux%zu)", level, cw, ch);
+    NvtxRange r_level(range_name);
+    stamp_level(0);
     const SolvePlan pl = plan_solve(h, g, p, median, slab_on);
     if (prev_slabbed && !pl.slabbed) return fail(h, FLOW2D_ERR_UNSUPPORTED, "slab: level %dx%d cannot be slabbed after a slabbed coarser level", g.w, g.h);
     // rows of this level on which the stages work: D = derivative planes, Wr = warped frame and flow
@@ -817,16 +856,26 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
       std::swap(u, u2); std::swap(v, v2);
     }
     if (njobs) {
+      NvtxRange r_res("flow2d: resample");
       launch_resample_batch(st, jobs, njobs, g.pitch);
       TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
     }
     // backward registration (344-363) and the level's derivative planes
-    launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g, W0, W1);
-    TRY(check_launch(h, FLOW2D_K_WARP, 1));
+    {
+      NvtxRange r_warp("flow2d: warp");
+      launch_warp(st, fr[0], fr[1], u, v, h->c[C_WARPED], g, W0, W1);
+      TRY(check_launch(h, FLOW2D_K_WARP, 1));
+    }
+    stamp_level(1);
     // solve (366-406)
     const int slot = h->iter_levels < FLOW2D_MAX_LEVELS ? h->iter_levels : FLOW2D_MAX_LEVELS - 1;
-    TRY(run_level_solve(h, g, fr[0], h->c[C_WARPED], u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI],
-                        h->c[C_KSI], residuals, p, pl, slot, D0, D1));
+    {
+      NvtxRange r_solve("flow2d: solve");
+      TRY(run_level_solve(h, g, fr[0], h->c[C_WARPED], u, v, h->c[C_DU0], h->c[C_DV0], h->c[C_DU1], h->c[C_DV1], h->c[C_PHI],
+                          h->c[C_KSI], residuals, p, pl, slot, D0, D1));
+    }
+    stamp_level(2);
+    if (level_times && h->timed_levels < FLOW2D_MAX_LEVELS) ++h->timed_levels;
     if (h->iter_levels < FLOW2D_MAX_LEVELS) ++h->iter_levels;
     if (residuals && h->residual_levels < FLOW2D_MAX_LEVELS && p->outer_iterations_count > 0 && p->inner_iterations_count > 0) {
       const bool ext = ext_solver(p);
@@ -844,6 +893,7 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
       const float* a[2] = {u, v};
       const float* b[2] = {h->c[C_DU0], h->c[C_DV0]};
       float* out[2] = {nu, nv};
+      NvtxRange r_med("flow2d: add + median");
       launch_add_median(st, a, b, out, 2, g.w, g.h, g.pitch, median, pl.Y0, pl.Y1);
       TRY(check_launch(h, FLOW2D_K_ADD_MEDIAN, 1));
       std::swap(u, u2); std::swap(v, v2);
@@ -916,7 +966,8 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   }
   TRY(ensure_ext(h, p));  // allocations of the opt-in extensions: never inside a stream capture
   static const bool no_graph = std::getenv("FLOW2D_NO_GRAPH") != nullptr;  // A/B switch for measurements
-  if (no_graph) return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+  // per-level timers are CUDA events between the stages: plain enqueue (the reference's timed path is not a graph either)
+  if (no_graph || p->report_level_times) return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
 
   GraphKey key;
   std::memset(&key, 0, sizeof key);
@@ -939,6 +990,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   for (auto& g : h->graphs)
     if (g.exec && std::memcmp(&key, g.key, sizeof key) == 0) slot = &g;
   if (slot) {
+    NvtxRange r_replay("flow2d: graph replay");
     CU_TRY(h, cudaGraphLaunch(slot->exec, h->stream));
     slot->last_use = ++h->graph_clock;
     ++h->graph_replays;
@@ -1042,6 +1094,7 @@ void flow2d_default_params(flow2d_params* p) {
   p->residual_tolerance = 0.f;
   p->residual_check_every = 0;
   p->cascaded_restriction = 0;
+  p->report_level_times = 0;
 }
 
 size_t flow2d_max_warp_level(size_t width, size_t height, float scale_factor) {
@@ -1111,6 +1164,11 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
   }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev_start) != cudaSuccess || cudaEventCreate(&h->ev_stop) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_in_ready[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_in_ready[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_in_free[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_in_free[1], cudaEventDisableTiming) != cudaSuccess ||
       solve_pass_configure() != cudaSuccess || solve_pass2_configure() != cudaSuccess || solve_pass3_configure() != cudaSuccess || cudaMemsetAsync(h->pool, 0, csize * ncont * sizeof(float), h->own_stream) != cudaSuccess ||
       cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
     (void)cudaGetLastError();
@@ -1127,6 +1185,11 @@ int flow2d_destroy(flow2d_handle* h) {
   if (!h) return FLOW2D_OK;
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (int i = 0; i < 2; i++) {
+    if (h->ev_in_ready[i]) cudaEventDestroy(h->ev_in_ready[i]);
+    if (h->ev_in_free[i]) cudaEventDestroy(h->ev_in_free[i]);
+  }
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -1143,6 +1206,7 @@ int flow2d_destroy(flow2d_handle* h) {
   if (h->d_stop) cudaFree(h->d_stop);
   if (h->d_partials) cudaFree(h->d_partials);
   if (h->d_counter) cudaFree(h->d_counter);
+  for (cudaEvent_t e : h->level_events) cudaEventDestroy(e);
   delete h;
   return FLOW2D_OK;
 }
@@ -1201,6 +1265,26 @@ int flow2d_level_outer_iterations(flow2d_handle* h, int* iterations, int capacit
   return FLOW2D_OK;
 }
 
+int flow2d_level_times(flow2d_handle* h, float* level_ms, float* solve_ms, int capacity, int* levels) {
+  STAGE_PROLOGUE(h);
+  if (levels) *levels = h->timed_levels;
+  if (h->timed_levels == 0 || capacity <= 0) return FLOW2D_OK;
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->timed_levels && i < capacity; i++) {
+    // a level ends where the next one starts; the last one with its solve (the final add + median is not timed)
+    float a = 0.f, b = 0.f;
+    const bool last = i + 1 >= h->timed_levels;
+    if (cudaEventElapsedTime(&a, h->level_events[3 * i], last ? h->level_events[3 * i + 2] : h->level_events[3 * (i + 1)]) != cudaSuccess ||
+        cudaEventElapsedTime(&b, h->level_events[3 * i + 1], h->level_events[3 * i + 2]) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return fail(h, FLOW2D_ERR_CUDA, "level timers not available");
+    }
+    if (level_ms) level_ms[i] = a;
+    if (solve_ms) solve_ms[i] = b;
+  }
+  return FLOW2D_OK;
+}
+
 int flow2d_stage_residual(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1_warped, const float* d_u,
                           const float* d_v, const float* d_du, const float* d_dv, const float* d_phi, const float* d_ksi,
                           size_t w, size_t hh, float hx, float hy, const flow2d_params* p, double* rms_u, double* rms_v) {
@@ -1250,18 +1334,26 @@ int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* fr
   CU_TRY(h, cudaSetDevice(h->device));
   reset_launch_counts(h);
   const size_t row = h->W * sizeof(float), dpitch = h->pitch * sizeof(float);
-  cudaStream_t st = h->stream;
-  CU_TRY(h, cudaEventRecord(h->ev_start, st));
-  // CopyData2DtoDevice (cuda_utils.cpp:66-84)
-  CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN0], dpitch, frame_0, row, row, h->H, cudaMemcpyHostToDevice, st));
-  CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN1], dpitch, frame_1, row, row, h->H, cudaMemcpyHostToDevice, st));
+  cudaStream_t st = h->stream, cs = h->copy_stream;
+  // CopyData2DtoDevice (cuda_utils.cpp:66-84), on the upload stream into the input set this call owns: the set is free
+  // once the call before the previous one has finished computing, so this upload runs while the previous call computes
+  const int set = (int)(h->async_calls++ & 1);
+  float* in0 = h->c[set ? C_IN2 : C_IN0];
+  float* in1 = h->c[set ? C_IN3 : C_IN1];
+  CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_in_free[set], 0));
+  CU_TRY(h, cudaEventRecord(h->ev_start, cs));
+  CU_TRY(h, cudaMemcpy2DAsync(in0, dpitch, frame_0, row, row, h->H, cudaMemcpyHostToDevice, cs));
+  CU_TRY(h, cudaMemcpy2DAsync(in1, dpitch, frame_1, row, row, h->H, cudaMemcpyHostToDevice, cs));
+  CU_TRY(h, cudaEventRecord(h->ev_in_ready[set], cs));
+  CU_TRY(h, cudaStreamWaitEvent(st, h->ev_in_ready[set], 0));
   float* out_u = h->c[C_OUT_U];
   float* out_v = h->c[C_OUT_V];
-  int rc = compute_on_device(h, h->c[C_IN0], h->c[C_IN1], out_u, out_v, p);
+  int rc = compute_on_device(h, in0, in1, out_u, out_v, p);
   if (rc != FLOW2D_OK) {
     cudaStreamSynchronize(st);
     return rc;
   }
+  CU_TRY(h, cudaEventRecord(h->ev_in_free[set], st));
   // CopyData2DFromDevice (cuda_utils.cpp:87-105)
   CU_TRY(h, cudaMemcpy2DAsync(flow_u, row, out_u, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaMemcpy2DAsync(flow_v, row, out_v, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));

@@ -216,7 +216,7 @@ int main(int argc, char** argv) {
   // Optional flags of the pair forms (none of them exists upstream; without them the program behaves like the
   // reference's): --residuals prints per-level residual norms; the rest switch on the opt-in solver extensions of
   // include/flow2d.h (flow2d_params.scheme ... cascaded_restriction).  Flags may stand anywhere and are removed from argv.
-  bool report_residuals = false, cascaded = false;
+  bool report_residuals = false, cascaded = false, level_times = false;
   int scheme = 0, data_term = 0, check_every = 0;
   float omega = 0.f, gamma = 0.f, tolerance = 0.f;
   {
@@ -230,6 +230,7 @@ int main(int argc, char** argv) {
       const char* v;
       if (a == "--residuals") report_residuals = true;
       else if (a == "--cascade") cascaded = true;
+      else if (a == "--level-times") level_times = true;
       else if ((v = val("--scheme="))) scheme = (string(v) == "rb" || string(v) == "red-black") ? 1 : 0;
       else if ((v = val("--omega="))) omega = (float)std::atof(v);
       else if ((v = val("--term="))) data_term = string(v) == "gradient" ? 1 : string(v) == "log" ? 2 : string(v) == "combined" ? 3 : 0;
@@ -342,6 +343,7 @@ int main(int argc, char** argv) {
   if (tolerance > 0.f) params.PushValuePtr("residual_tolerance", &tolerance);
   if (check_every > 0) params.PushValuePtr("residual_check_every", &check_every);
   if (cascaded) params.PushValuePtr("cascaded_restriction", &cascaded);
+  if (level_times) params.PushValuePtr("report_level_times", &level_times);
 
   flow_u.ZeroData();
   flow_v.ZeroData();

@@ -75,6 +75,8 @@ void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u
   if (void* opt = params.GetValuePtr("residual_tolerance")) p.residual_tolerance = *static_cast<float*>(opt);
   if (void* opt = params.GetValuePtr("residual_check_every")) p.residual_check_every = *static_cast<int*>(opt);
   if (void* opt = params.GetValuePtr("cascaded_restriction")) p.cascaded_restriction = *static_cast<bool*>(opt) ? 1 : 0;
+  // the reference times every level's solve and prints it unless `silent` (cuda_operation_solve_2d.cpp:302-311)
+  if (void* opt = params.GetValuePtr("report_level_times")) p.report_level_times = *static_cast<bool*>(opt) ? 1 : 0;
   for (Data2D* d : {&frame_0, &frame_1, &flow_u, &flow_v})
     if (d->Width() != size_.width || d->Height() != size_.height || !d->DataPtr()) {
       std::printf("Error: '%s': frames and flow fields must be %zux%zu.\n", GetName(), size_.width, size_.height);
@@ -91,6 +93,12 @@ void OpticalFlow2D::ComputeFlow(Data2D& frame_0, Data2D& frame_1, Data2D& flow_u
   int levels = 0;
   flow2d_last_stats(handle_, &launches, &levels, &last_gpu_time_ms);
   if (!silent) std::printf("Levels: %d, kernel launches: %lld\n", levels, launches);
+  if (p.report_level_times) {
+    float lv[FLOW2D_MAX_LEVELS], sv[FLOW2D_MAX_LEVELS];
+    int n = 0;
+    if (flow2d_level_times(handle_, lv, sv, FLOW2D_MAX_LEVELS, &n) == FLOW2D_OK)
+      for (int i = 0; i < n; i++) std::printf("Level %3d (coarsest first): %8.4fs, solve %8.4fs\n", i, lv[i] / 1000., sv[i] / 1000.);
+  }
   if (p.residual_tolerance > 0.f) {
     int it[FLOW2D_MAX_LEVELS], n = 0;
     if (flow2d_level_outer_iterations(handle_, it, FLOW2D_MAX_LEVELS, &n) == FLOW2D_OK) {

@@ -91,6 +91,9 @@ typedef struct flow2d_params {
   int    residual_check_every;   /* test after every n-th outer iteration (<= 0: every one) */
   int    cascaded_restriction;   /* 1: level l of the two frame pyramids is restricted from level l-1 (once, before the
                                     level loop) instead of from the full-resolution frame */
+  int    report_level_times;     /* opt-in diagnostics: 1 = time every level and its solve with CUDA events (the reference's
+                                    per-level solve timer, cuda_operation_solve_2d.cpp:214-220, 302-311); the schedule is then
+                                    enqueued kernel by kernel instead of replayed as a CUDA graph.  Results are unchanged */
 } flow2d_params;
 
 enum { FLOW2D_SCHEME_JACOBI = 0, FLOW2D_SCHEME_RED_BLACK = 1 };
@@ -134,8 +137,11 @@ FLOW2D_API int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, c
                           float* d_flow_u, float* d_flow_v, const flow2d_params* p);
 
 /* Asynchronous form of flow2d_compute for pipelines that keep several handles busy at once (one
- * stream each): enqueues H2D, the solve and D2H on the handle's stream and returns.  The host
- * buffers must be page-locked (flow2d_host_alloc) and stay untouched until flow2d_synchronize(). */
+ * stream each): enqueues H2D, the solve and D2H and returns.  The host buffers must be page-locked
+ * (flow2d_host_alloc) and stay untouched until flow2d_synchronize().  The two frames are uploaded
+ * on an internal copy stream into one of two input sets, starting at once -- their contents must be
+ * final when the call is made -- so that the upload of call n+1 overlaps the solve of call n on the
+ * same handle; the solve and the D2H are ordered on the handle's stream. */
 FLOW2D_API int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* frame_1,
                          float* flow_u, float* flow_v, const flow2d_params* p);
 FLOW2D_API int flow2d_synchronize(flow2d_handle* h);
@@ -177,6 +183,11 @@ FLOW2D_API int flow2d_stage_residual(flow2d_handle* h, const float* d_frame_0, c
                           const float* d_u, const float* d_v, const float* d_du, const float* d_dv,
                           const float* d_phi, const float* d_ksi, size_t w, size_t hh, float hx, float hy,
                           const flow2d_params* p, double* rms_u, double* rms_v);
+
+/* With flow2d_params.report_level_times = 1: device time in ms of every level of the last flow2d_compute*() call (from its
+ * first kernel to the first kernel of the next level) and of its solve alone, coarsest level first.  Replaces the per-level
+ * "solve" timer of the reference (cuda_operation_solve_2d.cpp:214-220, 302-311, printed when !silent).  Waits for the stream. */
+FLOW2D_API int flow2d_level_times(flow2d_handle* h, float* level_ms, float* solve_ms, int capacity, int* levels);
 
 /* Outer iterations that ran per level in the last flow2d_compute*() call, coarsest level first (equal to
  * outer_iterations_count unless residual_tolerance ended a level early).  Waits for the handle's stream. */

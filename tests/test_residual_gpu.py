@@ -75,3 +75,21 @@ def test_level_residuals_of_a_flow_and_results_unchanged(pkg, oracle, synth, tor
     assert np.array_equal(u2, u1)
     ou, ov = oracle.compute_flow(f0, f1, oracle.make_params(**cfg))
     assert np.array_equal(u1, ou) and np.array_equal(v1, ov)
+
+
+def test_level_times_and_results_unchanged(pkg, synth, torch_):
+    """flow2d_params.report_level_times: the reference's per-level solve timer (cuda_operation_solve_2d.cpp:302-311)."""
+    w, h = 320, 240
+    f0, f1, _, _ = synth.make_pair(w, h, 9, U1=2.0)
+    cfg = dict(levels=50, scale=0.8, outer=4, inner=5, alpha=20.0, median=3, sigma=1.0)
+    fl = pkg.Flow2D(w, h)
+    u0, v0 = fl.compute(f0, f1, pkg.default_params(**cfg))
+    assert fl.level_times() == []
+    p = pkg.default_params(**cfg)
+    p.report_level_times = 1
+    u1, v1 = fl.compute(f0, f1, p)
+    assert np.array_equal(u0, u1) and np.array_equal(v0, v1)
+    t = fl.level_times()
+    assert len(t) == fl.stats()["levels_run"]
+    assert all(lv > 0 and 0 < sv <= lv * 1.001 + 1e-3 for lv, sv in t), t
+    assert sum(lv for lv, _ in t) <= fl.stats()["device_ms"] * 1.01 + 0.05
