@@ -237,6 +237,7 @@ constexpr size_t kSlabRowsCap = 128;  // rows per message the mailbox can hold
 
 struct SolvePlan {
   int S = 1, npass = 1;
+  bool pad2 = false;                // solve_pass3: x halo rounded up to 2 columns (68-wide staging boxes) instead of to 4
   bool slabbed = false;
   int Y0 = 0, Y1 = 0;               // own rows
   int ghost = 0;                    // rows of du/dv received from each neighbour per exchange
@@ -251,23 +252,67 @@ void slab_own_rows(int h, int rank, int world, int* y0, int* y1) {
   *y1 = *y0 + base + (rank < extra ? 1 : 0);
 }
 
+// Which generation of the tiled pass a handle uses (A/B switches: FLOW2D_SOLVE_V1, FLOW2D_SOLVE_V2), and the x halo of its
+// region: S+1 columns rounded up to the 4 of an aligned float4 strip, or (solve_pass3: TMA boxes start anywhere) to 2.
+int tiled_generation(const flow2d_handle* h) {
+  static const bool v1 = std::getenv("FLOW2D_SOLVE_V1") != nullptr, v2 = std::getenv("FLOW2D_SOLVE_V2") != nullptr;
+  if (v1) return 1;
+  return (h->constancy == FLOW2D_GRADIENT || v2 || !h->pass3) ? 2 : 3;
+}
+int tiled_halo_x(bool pad2, int sweeps) { return pad2 ? ((sweeps + 2) & ~1) : ((sweeps + 1 <= 4) ? 4 : 8); }
+
+// Time model of one tile of a tiled pass in us, fitted on B200 (profiles/r02/pass3_ab): setup + hand-over of a pass that
+// computes phi / ksi (`first`) or reloads them, the 64-bit staging reads of a region that starts off a 16-byte boundary,
+// and 0.65 us per sweep.  solve_pass2: 4.9 / 3.7.
+double tile_us(int gen, bool first, int halo_x, int sweeps) {
+  if (gen != 3) return (first ? 4.9 : 3.7) + 0.65 * sweeps;
+  return (first ? 4.6 : 3.2) + ((halo_x & 2) ? (first ? 0.9 : 1.1) : 0.0) + 0.65 * sweeps;
+}
+
 SolvePlan plan_solve(const flow2d_handle* h, const LevelGeom& g, const flow2d_params* p, int median, bool allow_slab) {
   SolvePlan pl;
   const int inner = (int)p->inner_iterations_count;
   int S = p->sweeps_per_pass;
+  pl.pad2 = tiled_generation(h) == 3 && std::getenv("FLOW2D_P3_HALO4") == nullptr;
   if (S <= 0) {
-    // Pick the sweeps per pass that minimises the modelled solve time.  Measured on B200 with solve_pass2
-    // (tools/phase_timing.py, profiles/r02): per wave of CTAs a pass costs ~4.9 us of setup and hand-over when it
-    // computes phi/ksi, ~3.7 us when it reloads them, plus ~0.65 us per sweep; region 64 x 48, halo S+1 rows and
-    // 4 (S <= 3) or 8 columns per side.
+    // Pick the sweeps per pass that minimise the modelled time of one outer iteration (region 64 x 48, halo S+1 rows and
+    // S+1 columns rounded up to 4, or -- solve_pass3 -- to 2 with the unaligned staging boxes; 0.7 us per launch).
+    // Two models, A/B-measured on one box (profiles/r02/pass3_ab/geometry_ab.txt, C4 = 1024^2 pairs):
+    //   default      fractional waves, 2-column rounding wherever it differs: best for several pairs sharing the GPU, where
+    //                other streams fill the SMs a level leaves idle (batch 111.3 Mpix/s, one pair alone 15.46 ms)
+    //   FLOW2D_P3_MODEL=1  whole rounds of one tile per SM, rounding chosen per level: best for one pair at a time
+    //                (15.24 ms; batch 109.1 Mpix/s)
+    //   FLOW2D_P3_HALO4=1  never the 2-column rounding (batch 108.7 Mpix/s, 15.66 ms)
+    static const bool halo4 = std::getenv("FLOW2D_P3_HALO4") != nullptr;
+    static const bool rounds_model = std::getenv("FLOW2D_P3_MODEL") != nullptr;
+    const int gen = tiled_generation(h);
     double best = 1e300;
-    for (int s_ = 1; s_ <= FLOW2D_MAX_SWEEPS_PER_PASS; ++s_) {
-      const int np = (inner + s_ - 1) / s_;
-      const int ow = kSolveLW - 2 * ((s_ + 1 <= 4) ? 4 : 8), oh = kSolveLH - 2 * (s_ + 1);
-      double waves = (double)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) / (double)h->sm_count;
-      if (waves < 1.0) waves = 1.0;
-      const double cost = waves * (4.9 + (np - 1) * 3.7 + 0.65 * inner);
-      if (cost < best) { best = cost; S = s_; }
+    if (rounds_model) {
+      for (int s_ = 1; s_ <= FLOW2D_MAX_SWEEPS_PER_PASS; ++s_) {
+        for (int pad = 0; pad < ((gen == 3 && !halo4) ? 2 : 1); ++pad) {
+          const int np = (inner + s_ - 1) / s_;
+          const int hx = tiled_halo_x(pad != 0, s_);
+          if (pad && !(hx & 2)) continue;  // same geometry as pad = 0
+          const int ow = kSolveLW - 2 * hx, oh = kSolveLH - 2 * (s_ + 1);
+          const long long tiles = (long long)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh);
+          const double rounds = (double)((tiles + h->sm_count - 1) / h->sm_count);
+          const double cost = rounds * (tile_us(gen, true, hx, s_) + (np - 1) * tile_us(gen, false, hx, s_)) + 0.7 * np;
+          if (cost < best) { best = cost; S = s_; pl.pad2 = pad != 0; }
+        }
+      }
+    } else {
+      pl.pad2 = gen == 3 && !halo4;
+      for (int s_ = 1; s_ <= FLOW2D_MAX_SWEEPS_PER_PASS; ++s_) {
+        const int np = (inner + s_ - 1) / s_;
+        const int hx = tiled_halo_x(pl.pad2, s_);
+        const int ow = kSolveLW - 2 * hx, oh = kSolveLH - 2 * (s_ + 1);
+        double waves = (double)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) / (double)h->sm_count;
+        if (waves < 1.0) waves = 1.0;
+        // (a region that starts off a 16-byte boundary pays for its 64-bit staging reads: + 0.9 / 1.1 us per pass)
+        const double first = 4.9 + ((hx & 2) ? 0.9 : 0.0), later = 3.7 + ((hx & 2) ? 1.1 : 0.0);
+        const double cost = waves * (first + (np - 1) * later + 0.65 * inner);
+        if (cost < best) { best = cost; S = s_; }
+      }
     }
   }
   if (S > FLOW2D_MAX_SWEEPS_PER_PASS) S = FLOW2D_MAX_SWEEPS_PER_PASS;
@@ -598,7 +643,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
       a.phi_out = store_phi ? phi : nullptr; a.ksi_out = store_phi ? ksi : nullptr;
       a.sweeps = s;
       a.halo_y = s + 1;
-      a.halo_x = (s + 1 <= 4) ? 4 : 8;
+      a.halo_x = tiled_halo_x(pl.pad2, s);
       a.ow = kSolveLW - 2 * a.halo_x;
       a.oh = kSolveLH - 2 * a.halo_y;
       if (slabbed && pass > 0) {  // the very first pass starts from du = dv = 0, exact everywhere
@@ -637,11 +682,12 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
         }
       }
       if (!small) {
-        static const bool v1 = std::getenv("FLOW2D_SOLVE_V1") != nullptr;  // A/B switches: the earlier generations of the tiled kernel
-        static const bool v2 = std::getenv("FLOW2D_SOLVE_V2") != nullptr;
         const int tx = (g.w + a.ow - 1) / a.ow, ty = (vb - va + a.oh - 1) / a.oh;
-        if (v1) launch_solve_pass(h->stream, a, grad, tx, ty);
-        else if (grad || v2 || !h->pass3 || !launch_solve_pass3(h->stream, a, tx, ty, h->sm_count)) launch_solve_pass2(h->stream, a, grad, tx, ty);
+        const int gen = tiled_generation(h);
+        if (gen == 1) launch_solve_pass(h->stream, a, grad, tx, ty);
+        else if (gen == 2) launch_solve_pass2(h->stream, a, grad, tx, ty);
+        else if (!launch_solve_pass3(h->stream, a, tx, ty, h->sm_count))
+          return fail(h, FLOW2D_ERR_CUDA, "solve_pass3: tensor map or launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         TRY(check_launch(h, FLOW2D_K_SOLVE_PASS, 1));
       }
       cur_du = a.du_out; cur_dv = a.dv_out;

@@ -12,7 +12,9 @@
 //     tile (u, v, fx, fy, ft [, du, dv [, phi, ksi]]) are fetched as 64x48 boxes of tensor maps by ONE thread -- one
 //     cp.async.bulk.tensor per plane, completion counted on an mbarrier -- into staging planes of their own.  Cells of a
 //     box outside the level are filled with zeros by the hardware (they are inert: zero weights, ksi = 0, denominator 1,
-//     and no cell inside the image ever reads them), so border tiles need no clamped scalar loads;
+//     and no cell inside the image ever reads them), so border tiles need no clamped scalar loads.  A box may start at
+//     any column, so the x halo is S+1 rounded up to 2 instead of to the 4 columns of an aligned float4: with five
+//     sweeps per pass the output tile is 52 x 36 instead of 48 x 36 of the 64 x 48 region;
 //   * as soon as phase C has consumed the staging planes the loads of the NEXT tile are issued; they land while the
 //     sweeps of the current tile run.  solve_pass2 had one CTA per SM as well (168 registers x 384 threads), so nothing
 //     hid its load phase: ncu showed 18 % of its samples there, half of them waiting for memory, plus spills of
@@ -21,7 +23,7 @@
 //     the publish step of solve_pass2 (8 STS.128 per thread and one CTA barrier per pass) is gone; a later pass of an
 //     outer iteration reads the neighbours' phi from its staging plane as well.
 //
-// Shared memory: 6 work planes (72 KiB, as solve_pass2) + 9 staging planes (108 KiB) + the mbarrier.
+// Shared memory: 6 work planes (72 KiB, as solve_pass2) + 9 staging planes of 68 x 48 (115 KiB) + the mbarrier.
 #include <cuda.h>
 
 #include <type_traits>
@@ -37,13 +39,41 @@ constexpr int NT3 = (LH / 2) * (LW / 4);  // 384 threads
 enum {
   W_SU0 = 0, W_SV0, W_SU1, W_SV1,  // sweeps: double-buffered s_u = u+du, s_v = v+dv (read by the rows above / below)
   W_RU, W_RV,                      // thread-private: fast-path reciprocals of the two denominators
-  T_U, T_V, T_FX, T_FY, T_FT, T_DU, T_DV, T_PHI, T_KSI,  // staging planes, written by TMA only
-  kPlanes3,
+  kWorkPlanes,
   W_PHI = W_SU1                    // phase C (neighbour rows of phi, first pass of an outer iteration); sweep 1 is the first writer of SU1
 };
+enum { T_U = 0, T_V, T_FX, T_FY, T_FT, T_DU, T_DV, T_PHI, T_KSI, kStagePlanes };  // staging planes, written by TMA only
 constexpr unsigned kPlaneBytes = PL * 4;
+// A TMA box must start on a 16-byte boundary of its row, while the region of a tile starts at an EVEN column (x halo =
+// S+1 rounded up to 2).  When that column is not a multiple of 4 (PAD2: halo 2 or 6, i.e. 1, 4 or 5 sweeps per pass) a
+// staging plane is a 68 x 48 box that starts two columns left of the region: its rows are 272 bytes apart and the strips
+// in it only 8-byte aligned, so it is read with 64-bit shared loads (twice the instructions and, with lanes 16 bytes
+// apart, twice the wavefronts of an aligned LDS.128 -- measured 7 % of a pass, against 17 % fewer tiles).  Otherwise
+// the box is the region itself and is read like a work plane.
+template <bool PAD2> struct Stage {
+  static constexpr int TW = PAD2 ? LW + 4 : LW, TPL = TW * LH;
+  static constexpr unsigned kBytes = TPL * 4;  // 13056 = 102 * 128 | 12288
+};
+constexpr unsigned kMaxStageBytes = Stage<true>::kBytes;
 
-size_t solve_pass3_smem_bytes() { return (size_t)kPlaneBytes * kPlanes3 + 16; }
+size_t solve_pass3_smem_bytes() { return (size_t)kPlaneBytes * kWorkPlanes + (size_t)kMaxStageBytes * kStagePlanes + 16; }
+
+// four pixels of a staging plane: plane and row offset are immediates of ONE per-thread address (strip A, staging plane 0)
+template <bool PAD2, int PLANE, int DROW>
+__device__ __forceinline__ Q ldt(unsigned addr) {
+  Q q;
+  constexpr int OFF = (PLANE * Stage<PAD2>::TPL + DROW * Stage<PAD2>::TW) * 4;
+  if (PAD2) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + %3];" : "=f"(q.lo.x), "=f"(q.lo.y) : "r"(addr), "n"(OFF) : "memory");
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2 + %3];" : "=f"(q.hi.x), "=f"(q.hi.y) : "r"(addr), "n"(OFF + 8) : "memory");
+  } else {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %5];"
+                 : "=f"(q.lo.x), "=f"(q.lo.y), "=f"(q.hi.x), "=f"(q.hi.y)
+                 : "r"(addr), "n"(OFF)
+                 : "memory");
+  }
+  return q;
+}
 
 struct Pass3Maps {
   CUtensorMap m[9];  // u v fx fy ft du dv phi ksi (the staging planes in order); unused entries are copies of m[0]
@@ -67,7 +97,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
-// one 64x48 box of a plane: global (tensor map, element coordinates x, y; may lie partly or wholly outside) -> shared
+// one 68x48 box of a plane: global (tensor map, element coordinates x, y; may lie partly or wholly outside) -> shared
 __device__ __forceinline__ void tma_load_box(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
                "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(bar)
@@ -76,7 +106,8 @@ __device__ __forceinline__ void tma_load_box(unsigned dst, const CUtensorMap* ma
 
 struct Tile3 {
   int ox0, oy0, ox1, oy1;  // output tile
-  int gx0, gy0;            // region origin (may be negative)
+  int gx0, gy0;            // region origin (may be negative; gx0 is even)
+  int bx0;                 // first column of the staged box: gx0 rounded down to a multiple of 4
   bool border;
 };
 __device__ __forceinline__ Tile3 tile_of(const SolveArgs& a, int tile, int tiles_x) {
@@ -85,22 +116,25 @@ __device__ __forceinline__ Tile3 tile_of(const SolveArgs& a, int tile, int tiles
   t.ox0 = bx * a.ow; t.oy0 = a.y0 + by * a.oh;
   t.ox1 = min(a.w, t.ox0 + a.ow); t.oy1 = min(a.y1, t.oy0 + a.oh);
   t.gx0 = t.ox0 - a.halo_x; t.gy0 = t.oy0 - a.halo_y;
+  t.bx0 = t.gx0 - (a.halo_x & 2);  // ox0 is a multiple of 4 (ow = 64 - 2 * halo_x, halo_x even)
   t.border = t.gx0 <= 0 || t.gx0 + LW >= a.w || t.gy0 <= 0 || t.gy0 + LH >= a.h;
   return t;
 }
 
 // phases A - E of one tile; the staging planes hold its inputs.  Returns after the stores of the tile.
 // `issue_next` is called by thread 0 once the staging planes are free again (after the barrier that ends phase C).
-template <bool BORDER, typename IssueNext>
-__device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, unsigned smem0, IssueNext issue_next) {
+template <bool BORDER, bool PAD2, typename IssueNext>
+__device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, unsigned smem0, unsigned stage0, IssueNext issue_next) {
   const int tid = threadIdx.x;
   const int trow = tid >> 4;      // thread row: region rows 2*trow (strip A) and 2*trow + 1 (strip B)
   const int lx = 4 * (tid & 15);  // first column of the strips within the region
   const int w = a.w, h = a.h, pitch = a.pitch;
   const int ox0 = tl.ox0, oy0 = tl.oy0, ox1 = tl.ox1, oy1 = tl.oy1;
-  const int gx = tl.gx0 + lx;  // multiple of 4
+  const int gx = tl.gx0 + lx;  // even (a TMA box may start at any column: the halo is S+1 rounded up to 2, not to 4)
   const int gyA = tl.gy0 + 2 * trow, gyB = gyA + 1;
-  const unsigned sb = keep(smem0 + 4u * (unsigned)(2 * trow * LW + lx));  // strip A, plane 0
+  const unsigned sb = keep(smem0 + 4u * (unsigned)(2 * trow * LW + lx));  // strip A, work plane 0
+  constexpr int TW = Stage<PAD2>::TW;
+  const unsigned tb = keep(stage0 + 4u * (unsigned)(2 * trow * TW + (PAD2 ? 2 : 0) + lx));  // strip A, staging plane 0
   constexpr int kLastT = LH / 2 - 1;
   // neighbour rows as in solve_pass2: the row above A and the row below B (the other two are the thread's own strips);
   // BORDER tiles take all four through run-time row offsets with the image-border mirror folded in
@@ -113,7 +147,7 @@ __device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, 
   }
   const unsigned a_upA = keep(sb + 4u * (unsigned)(upA * LW)), a_dnB = keep(sb + 4u * (unsigned)(dnB * LW));
   const unsigned a_dnA = BORDER ? keep(sb + 4u * (unsigned)(dnA * LW)) : sb, a_upB = BORDER ? keep(sb + 4u * (unsigned)(upB * LW)) : sb;
-  const bool x_lo = BORDER && gx == 0;        // only element 0 of a strip can be x == 0 (gx % 4 == 0)
+  const int x_lo = BORDER ? -gx : -1;         // element index of x == 0 in this strip, if 0..3
   const int i_hi = BORDER ? w - 1 - gx : -1;  // element index of x == w-1 in this strip, if 0..3
   bool insA[4], insB[4];                      // cells outside the image exist only in BORDER tiles
 #pragma unroll
@@ -130,20 +164,20 @@ __device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, 
   Q J11A, J22A, J11B, J22B;
   // ------ phase A: own cells from the staging planes; ksi (solve_2d.cu:176-196); motion tensor ------
   {
-    A.uc = ldsq<T_U, 0>(sb); B.uc = ldsq<T_U, 1>(sb);
-    A.vc = ldsq<T_V, 0>(sb); B.vc = ldsq<T_V, 1>(sb);
-    const Q fxA = ldsq<T_FX, 0>(sb), fxB = ldsq<T_FX, 1>(sb);
-    const Q fyA = ldsq<T_FY, 0>(sb), fyB = ldsq<T_FY, 1>(sb);
-    const Q ftA = ldsq<T_FT, 0>(sb), ftB = ldsq<T_FT, 1>(sb);
+    A.uc = ldt<PAD2, T_U, 0>(tb); B.uc = ldt<PAD2, T_U, 1>(tb);
+    A.vc = ldt<PAD2, T_V, 0>(tb); B.vc = ldt<PAD2, T_V, 1>(tb);
+    const Q fxA = ldt<PAD2, T_FX, 0>(tb), fxB = ldt<PAD2, T_FX, 1>(tb);
+    const Q fyA = ldt<PAD2, T_FY, 0>(tb), fyB = ldt<PAD2, T_FY, 1>(tb);
+    const Q ftA = ldt<PAD2, T_FT, 0>(tb), ftB = ldt<PAD2, T_FT, 1>(tb);
     if (a.du_in) {
-      duA = ldsq<T_DU, 0>(sb); duB = ldsq<T_DU, 1>(sb);
-      A.dv = ldsq<T_DV, 0>(sb); B.dv = ldsq<T_DV, 1>(sb);
+      duA = ldt<PAD2, T_DU, 0>(tb); duB = ldt<PAD2, T_DU, 1>(tb);
+      A.dv = ldt<PAD2, T_DV, 0>(tb); B.dv = ldt<PAD2, T_DV, 1>(tb);
     } else {
       duA = duB = A.dv = B.dv = qsplat(0.f);
     }
     if (later) {
-      phiA = ldsq<T_PHI, 0>(sb); phiB = ldsq<T_PHI, 1>(sb);
-      A.ksi = ldsq<T_KSI, 0>(sb); B.ksi = ldsq<T_KSI, 1>(sb);
+      phiA = ldt<PAD2, T_PHI, 0>(tb); phiB = ldt<PAD2, T_PHI, 1>(tb);
+      A.ksi = ldt<PAD2, T_KSI, 0>(tb); B.ksi = ldt<PAD2, T_KSI, 1>(tb);
     }
     auto tensor_ksi = [&](const Q& fx, const Q& fy, const Q& ft, const Q& d_u, const Q& d_v, Strip2& t, Q& J11o, Q& J22o) {
       const Q J11 = qmul(fx, fx), J22 = qmul(fy, fy), J12 = qmul(fx, fy);
@@ -182,6 +216,9 @@ __device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, 
   }
 
   Q pU_A, pD_A, pU_B, pD_B;  // phi of the rows above / below the two strips
+  // the same neighbour rows in the staging planes
+  const unsigned t_upA = tb + 4u * (unsigned)(upA * TW), t_dnB = tb + 4u * (unsigned)(dnB * TW);
+  const unsigned t_dnA = tb + 4u * (unsigned)(dnA * TW), t_upB = tb + 4u * (unsigned)(upB * TW);
   if (!later) {
     // ---------------- phase B: phi (solve_2d.cu:141-162); neighbour rows straight from the staging planes ----------------
     const float hx2 = a.hx + a.hx, hy2 = a.hy + a.hy;
@@ -191,14 +228,14 @@ __device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, 
     auto ynum = [&](auto plane_f, auto plane_d, const Q& fA, const Q& fB, const Q& dA_, const Q& dB_, Q& nA, Q& nB) {
       constexpr int PF = decltype(plane_f)::value, PD = decltype(plane_d)::value;
       Q fU_A, fD_A, fU_B, fD_B, dU_A, dD_A, dU_B, dD_B;
-      fU_A = ldsq_at<PF>(a_upA); fD_B = ldsq_at<PF>(a_dnB);
-      if (have_d) { dU_A = ldsq_at<PD>(a_upA); dD_B = ldsq_at<PD>(a_dnB); }
+      fU_A = ldt<PAD2, PF, 0>(t_upA); fD_B = ldt<PAD2, PF, 0>(t_dnB);
+      if (have_d) { dU_A = ldt<PAD2, PD, 0>(t_upA); dD_B = ldt<PAD2, PD, 0>(t_dnB); }
       else dU_A = dD_B = qsplat(0.f);
       if (!BORDER) {
         fD_A = fB; dD_A = dB_; fU_B = fA; dU_B = dA_;  // the other strip of this thread
       } else {
-        fD_A = ldsq_at<PF>(a_dnA); fU_B = ldsq_at<PF>(a_upB);
-        if (have_d) { dD_A = ldsq_at<PD>(a_dnA); dU_B = ldsq_at<PD>(a_upB); }
+        fD_A = ldt<PAD2, PF, 0>(t_dnA); fU_B = ldt<PAD2, PF, 0>(t_upB);
+        if (have_d) { dD_A = ldt<PAD2, PD, 0>(t_dnA); dU_B = ldt<PAD2, PD, 0>(t_upB); }
         else dD_A = dU_B = qsplat(0.f);
       }
       nA = qsub(qadd(qsub(fD_A, fU_A), dD_A), dU_A);
@@ -249,9 +286,9 @@ __device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, 
     if (!BORDER) { pD_A = phiB; pU_B = phiA; }
     else { pD_A = ldsq_at<W_PHI>(a_dnA); pU_B = ldsq_at<W_PHI>(a_upB); }
   } else {
-    pU_A = ldsq_at<T_PHI>(a_upA); pD_B = ldsq_at<T_PHI>(a_dnB);
+    pU_A = ldt<PAD2, T_PHI, 0>(t_upA); pD_B = ldt<PAD2, T_PHI, 0>(t_dnB);
     if (!BORDER) { pD_A = phiB; pU_B = phiA; }
-    else { pD_A = ldsq_at<T_PHI>(a_dnA); pU_B = ldsq_at<T_PHI>(a_upB); }
+    else { pD_A = ldt<PAD2, T_PHI, 0>(t_dnA); pU_B = ldt<PAD2, T_PHI, 0>(t_upB); }
   }
 
   // ---------------- phase C: weights and denominators (solve_2d.cu:333-349, 363, 367) ----------------
@@ -413,16 +450,17 @@ __device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, 
     if (gy >= oy0 && gy < oy1) {
       float* rdu = a.du_out + (size_t)gy * pitch;
       float* rdvp = a.dv_out + (size_t)gy * pitch;
-      float d1[4], d2[4];
-      qarr(du_, d1); qarr(dv_, d2);
-      if (gx >= ox0 && gx + 3 < ox1) {
-        st4(rdu + gx, d1);
-        st4(rdvp + gx, d2);
-      } else {
+      // gx is even and rows are 16-byte aligned: the pairs (gx, gx+1) and (gx+2, gx+3) are aligned float2s
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int x = gx + i;
-          if (x >= ox0 && x < ox1) { rdu[x] = d1[i]; rdvp[x] = d2[i]; }
+      for (int k = 0; k < 2; k++) {
+        const int x = gx + 2 * k;
+        const float2 pu = k ? du_.hi : du_.lo, pv = k ? dv_.hi : dv_.lo;
+        if (x >= ox0 && x + 1 < ox1) {
+          *reinterpret_cast<float2*>(rdu + x) = pu;
+          *reinterpret_cast<float2*>(rdvp + x) = pv;
+        } else {
+          if (x >= ox0 && x < ox1) { rdu[x] = pu.x; rdvp[x] = pv.x; }
+          if (x + 1 >= ox0 && x + 1 < ox1) { rdu[x + 1] = pu.y; rdvp[x + 1] = pv.y; }
         }
       }
     }
@@ -431,11 +469,14 @@ __device__ __forceinline__ void pass3_tile(const SolveArgs& a, const Tile3& tl, 
   store(gyB, duB, B.dv);
 }
 
+template <bool PAD2>
 __global__ void __launch_bounds__(NT3, 1) solve_pass3_kernel(const SolveArgs a, const __grid_constant__ Pass3Maps maps, int tiles_x, int tiles) {
+  constexpr unsigned kStageBytes = Stage<PAD2>::kBytes;
   extern __shared__ __align__(128) float sm[];
   if (a.stop && *a.stop) return;  // the level has converged (flow2d_params.residual_tolerance)
   const unsigned smem0 = (unsigned)__cvta_generic_to_shared(sm);
-  const unsigned bar = smem0 + kPlaneBytes * kPlanes3;
+  const unsigned stage0 = smem0 + kPlaneBytes * kWorkPlanes;
+  const unsigned bar = stage0 + kMaxStageBytes * kStagePlanes;
   const int tid = threadIdx.x;
   const bool later = a.phi_in != nullptr, have_d = a.du_in != nullptr;
   const unsigned nplanes = later ? 9u : have_d ? 7u : 5u;
@@ -452,17 +493,17 @@ __global__ void __launch_bounds__(NT3, 1) solve_pass3_kernel(const SolveArgs a, 
   auto issue = [&](int t, bool first) {
     const Tile3 tl = tile_of(a, t, tiles_x);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the staging planes
-    mbar_expect_tx(bar, nplanes * kPlaneBytes);
+    mbar_expect_tx(bar, nplanes * kStageBytes);
 #pragma unroll
-    for (int p = 0; p < 5; p++) tma_load_box(smem0 + (T_U + p) * kPlaneBytes, &maps.m[p], tl.gx0, tl.gy0, bar);
+    for (int p = 0; p < 5; p++) tma_load_box(stage0 + (T_U + p) * kStageBytes, &maps.m[p], tl.bx0, tl.gy0, bar);
     if (first && a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (have_d) {
-      tma_load_box(smem0 + T_DU * kPlaneBytes, &maps.m[5], tl.gx0, tl.gy0, bar);
-      tma_load_box(smem0 + T_DV * kPlaneBytes, &maps.m[6], tl.gx0, tl.gy0, bar);
+      tma_load_box(stage0 + T_DU * kStageBytes, &maps.m[5], tl.bx0, tl.gy0, bar);
+      tma_load_box(stage0 + T_DV * kStageBytes, &maps.m[6], tl.bx0, tl.gy0, bar);
     }
     if (later) {
-      tma_load_box(smem0 + T_PHI * kPlaneBytes, &maps.m[7], tl.gx0, tl.gy0, bar);
-      tma_load_box(smem0 + T_KSI * kPlaneBytes, &maps.m[8], tl.gx0, tl.gy0, bar);
+      tma_load_box(stage0 + T_PHI * kStageBytes, &maps.m[7], tl.bx0, tl.gy0, bar);
+      tma_load_box(stage0 + T_KSI * kStageBytes, &maps.m[8], tl.bx0, tl.gy0, bar);
     }
   };
   if (tid == 0) issue(tile, true);
@@ -476,14 +517,16 @@ __global__ void __launch_bounds__(NT3, 1) solve_pass3_kernel(const SolveArgs a, 
     };
     mbar_wait(bar, parity);
     parity ^= 1u;
-    if (tl.border) pass3_tile<true>(a, tl, smem0, issue_next);
-    else pass3_tile<false>(a, tl, smem0, issue_next);
+    if (tl.border) pass3_tile<true, PAD2>(a, tl, smem0, stage0, issue_next);
+    else pass3_tile<false, PAD2>(a, tl, smem0, stage0, issue_next);
     __syncthreads();  // the work planes are free for the next tile
   }
 }
 
 cudaError_t solve_pass3_configure() {
-  return cudaFuncSetAttribute(solve_pass3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_pass3_smem_bytes());
+  cudaError_t e = cudaFuncSetAttribute(solve_pass3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_pass3_smem_bytes());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(solve_pass3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_pass3_smem_bytes());
+  return e;
 }
 
 // ---- host side: tensor maps (one per input plane of the launch) ----
@@ -503,12 +546,12 @@ EncodeTiledFn encode_tiled() {
   }();
   return fn;
 }
-bool make_map(CUtensorMap* m, const float* plane, int w, int h, int pitch) {
+bool make_map(CUtensorMap* m, const float* plane, int w, int h, int pitch, int box_w) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
   const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)LW, (cuuint32_t)LH}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)LH}, estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(plane), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -520,8 +563,9 @@ bool solve_pass3_available() { return encode_tiled() != nullptr; }
 bool launch_solve_pass3(cudaStream_t st, const SolveArgs& a, int grid_x, int grid_y, int ctas) {
   Pass3Maps maps;
   const float* planes[9] = {a.u, a.v, a.fx, a.fy, a.ft, a.du_in, a.dv_in, a.phi_in, a.ksi_in};
+  const bool pad2 = (a.halo_x & 2) != 0;  // the region starts two columns right of a 16-byte boundary
   for (int i = 0; i < 9; i++)
-    if (!make_map(&maps.m[i], planes[i] ? planes[i] : a.u, a.w, a.h, a.pitch)) return false;
+    if (!make_map(&maps.m[i], planes[i] ? planes[i] : a.u, a.w, a.h, a.pitch, pad2 ? Stage<true>::TW : Stage<false>::TW)) return false;
   const int tiles = grid_x * grid_y;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas < tiles ? ctas : tiles);
@@ -533,12 +577,14 @@ bool launch_solve_pass3(cudaStream_t st, const SolveArgs& a, int grid_x, int gri
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = a.pdl ? 1 : 0;  // only between consecutive passes of one solve (see SolveArgs::pdl)
-  return cudaLaunchKernelEx(&cfg, solve_pass3_kernel, a, maps, grid_x, tiles) == cudaSuccess;
+  if (pad2) return cudaLaunchKernelEx(&cfg, solve_pass3_kernel<true>, a, maps, grid_x, tiles) == cudaSuccess;
+  return cudaLaunchKernelEx(&cfg, solve_pass3_kernel<false>, a, maps, grid_x, tiles) == cudaSuccess;
 }
 
 void preload_solve_pass3_kernels() {
   cudaFuncAttributes at;
-  cudaFuncGetAttributes(&at, solve_pass3_kernel);
+  cudaFuncGetAttributes(&at, solve_pass3_kernel<false>);
+  cudaFuncGetAttributes(&at, solve_pass3_kernel<true>);
 }
 
 }  // namespace flow2d

@@ -1,0 +1,9 @@
+#!/bin/bash
+OUT=gpurun_out/${1:-p3d}; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_flow_gpu.py tests/test_stages_gpu.py tests/test_native_sizes_gpu.py tests/test_reference_gpu.py tests/test_ext_gpu.py tests/test_slab_gpu.py -m gpu -q -x --timeout 300 2>&1 | tail -4 | tee $OUT/pytest.log
+for wl in c2 c4s c4 c3 c1b; do
+    args="--workload $wl"; [ $wl = c4s ] && args="--workload c4 --streams 1 --pairs 1"
+    timeout 300 python bench.py $args --steps 5 --warmup 3 --no-extra 2>$OUT/err_${wl}.txt | tail -1 > $OUT/bench_${wl}.json
+    python -c "
+import json; d=json.load(open('$OUT/bench_${wl}.json')); print('$wl value %.1f e2e %.1f ms/step %.3f launch_us %.2f'%(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['launch_us']))" || tail -3 $OUT/err_${wl}.txt
+done
