@@ -88,6 +88,11 @@ struct flow2d_handle {
   float* J6[6] = {};
   float* pyr_pool = nullptr;      // cascaded restriction: levels 1.. of both frame pyramids, row after row at the handle's pitch
   size_t pyr_rows = 0;            // rows per frame the pool holds
+  // Both frame pyramids are flow-independent: they are restricted on a stream of their own, ahead of the level loop
+  // (which waits, level by level, for an event), into pyr_pool; the coarse levels' long, latency-bound restriction
+  // kernels then overlap the coarse levels' solves instead of sitting between them
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> pyr_events;  // [0]: fork, [l]: level l of both pyramids is ready
   int* d_stop = nullptr;          // FLOW2D_MAX_LEVELS stop words, then FLOW2D_MAX_LEVELS iteration counts
   double* d_partials = nullptr;   // per-CTA partial sums of the convergence test
   unsigned* d_counter = nullptr;
@@ -446,7 +451,17 @@ int ensure_ext(flow2d_handle* h, const flow2d_params* p) {
     CU_TRY(h, cudaMemset(h->d_stop, 0, sizeof(int) * 2 * FLOW2D_MAX_LEVELS));
     CU_TRY(h, cudaMemset(h->d_counter, 0, sizeof(unsigned)));
   }
-  if (p->cascaded_restriction) {
+  static const bool no_side = std::getenv("FLOW2D_NO_SIDE_PYRAMID") != nullptr;  // A/B switch: restrict inside the level loop
+  const bool side = !no_side && !p->cascaded_restriction && levels_of(h, p) > 1;
+  if (side) {
+    if (!h->side_stream) CU_TRY(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    while ((int)h->pyr_events.size() < levels_of(h, p) + 1) {
+      cudaEvent_t e = nullptr;
+      CU_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->pyr_events.push_back(e);
+    }
+  }
+  if (p->cascaded_restriction || side) {
     const size_t rows = pyramid_rows(h, p, levels_of(h, p), nullptr);
     if (rows > h->pyr_rows) {
       CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -857,6 +872,27 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     }
   }
 
+  // default: every level of both pyramids from the full-resolution frames (optical_flow_2d.cpp:279-305), on the side
+  // stream, coarsest level first (the order in which the loop below consumes them)
+  static const bool no_side = std::getenv("FLOW2D_NO_SIDE_PYRAMID") != nullptr;
+  const bool side = !no_side && !slab_on && !cascade && level >= 1 && level < FLOW2D_MAX_LEVELS + 63 && h->side_stream &&
+                    (int)h->pyr_events.size() > level && h->pyr_rows >= pyramid_rows(h, p, level + 1, nullptr);
+  if (side) {
+    NvtxRange r_pyr("flow2d: frame pyramids (side stream)");
+    pyramid_rows(h, p, level + 1, pyr_row_of);
+    CU_TRY(h, cudaEventRecord(h->pyr_events[0], st));
+    CU_TRY(h, cudaStreamWaitEvent(h->side_stream, h->pyr_events[0], 0));
+    for (int l = level; l >= 1; --l) {
+      size_t cw, ch; float hx, hy;
+      flow2d_level_geometry(W, H, p->warp_scale_factor, l, &cw, &ch, &hx, &hy);
+      ResampleJob jb[2];
+      for (int i = 0; i < 2; i++) jb[i] = ResampleJob{frame[i], h->c[C_RES0 + i], pyr_level(i, l), (int)W, (int)H, (int)cw, (int)ch, 0, 0, 0, 0, 0};
+      launch_resample_batch(h->side_stream, jb, 2, (int)h->pitch);
+      TRY(check_launch(h, FLOW2D_K_RESAMPLE, 2));
+      CU_TRY(h, cudaEventRecord(h->pyr_events[l], h->side_stream));
+    }
+  }
+
   while (level >= 0) {
     size_t cw, ch;
     float hx, hy;
@@ -885,8 +921,9 @@ int enqueue_pyramid(flow2d_handle* h, const float* frame_0, const float* frame_1
     const float* fr[2] = {frame[0], frame[1]};
     ResampleJob jobs[4];
     int njobs = 0;
-    if (level != 0 && cascade) {
+    if (level != 0 && (cascade || side)) {
       fr[0] = pyr_level(0, level); fr[1] = pyr_level(1, level);
+      if (side) CU_TRY(h, cudaStreamWaitEvent(st, h->pyr_events[level], 0));
     } else if (level != 0) {
       // (frame 1 is needed wherever the flow may point: all rows; frame 0 on the rows that are warped / differentiated)
       jobs[njobs++] = ResampleJob{frame[0], h->c[C_TMP0], h->c[C_RES0], (int)W, (int)H, g.w, g.h, W0, W1, 0, 0, 0};
@@ -1253,6 +1290,8 @@ int flow2d_destroy(flow2d_handle* h) {
   if (h->d_partials) cudaFree(h->d_partials);
   if (h->d_counter) cudaFree(h->d_counter);
   for (cudaEvent_t e : h->level_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->pyr_events) cudaEventDestroy(e);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   delete h;
   return FLOW2D_OK;
 }
