@@ -34,8 +34,17 @@ PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_c4.csv python tools/profile_step.py c4 0 1 > $OUT/ncu_c4.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 78 -c 78 --csv --log-file $OUT/launches_c2.csv python tools/profile_step.py c2 1 1 > $OUT/ncu_c2.log 2>&1
 # full captures
-ncu --set full --clock-control none --import-source on -k regex:solve_pass -s 40 -c 1 -o $OUT/solve_c2 python tools/profile_step.py c2 0 1 > $OUT/ncu_full_c2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:solve_pass -s 2 -c 1 -o $OUT/solve_2048 python tools/profile_stages.py 2048 2048 > $OUT/ncu_full_2048.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:solve_pass3 -s 40 -c 1 -o $OUT/solve_c2 python tools/profile_step.py c2 0 1 > $OUT/ncu_full_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:solve_pass3 -s 540 -c 1 -o $OUT/solve_c4 python tools/profile_step.py c4 0 1 > $OUT/ncu_full_c4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:solve_pass3 -s 2 -c 1 -o $OUT/solve_2048 python tools/profile_stages.py 2048 2048 > $OUT/ncu_full_2048.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:solve_small -s 700 -c 1 -o $OUT/solve_small python tools/profile_step.py c4 0 1 > $OUT/ncu_full_small.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:warp_kernel -c 1 -o $OUT/warp_2048 python tools/profile_stages.py 2048 2048 > $OUT/ncu_full_warp.log 2>&1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $OUT/stages_2048.csv python tools/profile_stages.py 2048 2048 > $OUT/stages.log 2>&1
+mkdir -p $OUT/sanitizer
+for t in memcheck racecheck; do
+  timeout 600 compute-sanitizer --tool $t python tools/sanitize.py > $OUT/sanitizer/$t.log 2>&1
+  grep -E "SUMMARY|^ok|done" $OUT/sanitizer/$t.log > $OUT/sanitizer/$t.txt
+done
+cat $OUT/sanitizer/*.txt | grep -E "SUMMARY|done"
+timeout 300 python tools/bench_sequence.py 64 8 2>/dev/null | tail -1 > $OUT/sequence_h8.json
 ls -la $OUT
