@@ -37,7 +37,7 @@ enum Container {
   C_FX, C_FY, C_FT,
   C_TMP0, C_TMP1,      // x-pass results of the resampler
   C_OUT_U, C_OUT_V,    // final flow of flow2d_compute (host API)
-  C_IN2, C_IN3,        // second set of uploaded frames: flow2d_compute_async uploads call n+1 while call n computes
+  C_IN2, C_IN3,        // landing pair of the uploads: flow2d_compute_async uploads call n+1 while call n computes
   C_J0, C_J1, C_J2, C_J3, C_J4,  // gradient mode only
   C_COUNT
 };
@@ -50,8 +50,8 @@ struct flow2d_handle {
   int constancy = FLOW2D_GREY;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-  // host API: the frames of a call are uploaded on a stream of their own into one of two input sets, so the upload of
-  // the next call overlaps the computation of the current one (a sequence through one handle, several handles per GPU)
+  // host API: the frames of a call are uploaded on a stream of their own into a landing pair, so the upload of the next
+  // call overlaps the computation of the current one (a sequence through one handle, several handles per GPU)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
   unsigned long long async_calls = 0;
@@ -1420,25 +1420,29 @@ int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* fr
   reset_launch_counts(h);
   const size_t row = h->W * sizeof(float), dpitch = h->pitch * sizeof(float);
   cudaStream_t st = h->stream, cs = h->copy_stream;
-  // CopyData2DtoDevice (cuda_utils.cpp:66-84), on the upload stream into the input set this call owns: the set is free
-  // once the call before the previous one has finished computing, so this upload runs while the previous call computes
-  const int set = (int)(h->async_calls++ & 1);
-  float* in0 = h->c[set ? C_IN2 : C_IN0];
-  float* in1 = h->c[set ? C_IN3 : C_IN1];
-  CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_in_free[set], 0));
+  // CopyData2DtoDevice (cuda_utils.cpp:66-84) on the upload stream into a landing pair; the handle's stream moves the
+  // frames from there into its fixed input pair (two device-to-device copies, microseconds) and frees the landing pair at
+  // once, so the upload of the next call runs while this one computes -- and the captured schedule, which reads the fixed
+  // pair, is the same graph for every call
+  float* land0 = h->c[C_IN2];
+  float* land1 = h->c[C_IN3];
+  ++h->async_calls;
+  CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_in_free[0], 0));
   CU_TRY(h, cudaEventRecord(h->ev_start, cs));
-  CU_TRY(h, cudaMemcpy2DAsync(in0, dpitch, frame_0, row, row, h->H, cudaMemcpyHostToDevice, cs));
-  CU_TRY(h, cudaMemcpy2DAsync(in1, dpitch, frame_1, row, row, h->H, cudaMemcpyHostToDevice, cs));
-  CU_TRY(h, cudaEventRecord(h->ev_in_ready[set], cs));
-  CU_TRY(h, cudaStreamWaitEvent(st, h->ev_in_ready[set], 0));
+  CU_TRY(h, cudaMemcpy2DAsync(land0, dpitch, frame_0, row, row, h->H, cudaMemcpyHostToDevice, cs));
+  CU_TRY(h, cudaMemcpy2DAsync(land1, dpitch, frame_1, row, row, h->H, cudaMemcpyHostToDevice, cs));
+  CU_TRY(h, cudaEventRecord(h->ev_in_ready[0], cs));
+  CU_TRY(h, cudaStreamWaitEvent(st, h->ev_in_ready[0], 0));
+  CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN0], dpitch, land0, dpitch, row, h->H, cudaMemcpyDeviceToDevice, st));
+  CU_TRY(h, cudaMemcpy2DAsync(h->c[C_IN1], dpitch, land1, dpitch, row, h->H, cudaMemcpyDeviceToDevice, st));
+  CU_TRY(h, cudaEventRecord(h->ev_in_free[0], st));
   float* out_u = h->c[C_OUT_U];
   float* out_v = h->c[C_OUT_V];
-  int rc = compute_on_device(h, in0, in1, out_u, out_v, p);
+  int rc = compute_on_device(h, h->c[C_IN0], h->c[C_IN1], out_u, out_v, p);
   if (rc != FLOW2D_OK) {
     cudaStreamSynchronize(st);
     return rc;
   }
-  CU_TRY(h, cudaEventRecord(h->ev_in_free[set], st));
   // CopyData2DFromDevice (cuda_utils.cpp:87-105)
   CU_TRY(h, cudaMemcpy2DAsync(flow_u, row, out_u, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaMemcpy2DAsync(flow_v, row, out_v, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));

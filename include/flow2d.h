@@ -139,9 +139,9 @@ FLOW2D_API int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, c
 /* Asynchronous form of flow2d_compute for pipelines that keep several handles busy at once (one
  * stream each): enqueues H2D, the solve and D2H and returns.  The host buffers must be page-locked
  * (flow2d_host_alloc) and stay untouched until flow2d_synchronize().  The two frames are uploaded
- * on an internal copy stream into one of two input sets, starting at once -- their contents must be
- * final when the call is made -- so that the upload of call n+1 overlaps the solve of call n on the
- * same handle; the solve and the D2H are ordered on the handle's stream. */
+ * on an internal copy stream into a landing pair, starting at once -- their contents must be final
+ * when the call is made -- so that the upload of call n+1 overlaps the solve of call n on the same
+ * handle; the solve and the D2H are ordered on the handle's stream. */
 FLOW2D_API int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* frame_1,
                          float* flow_u, float* flow_v, const flow2d_params* p);
 FLOW2D_API int flow2d_synchronize(flow2d_handle* h);
