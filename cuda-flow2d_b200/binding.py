@@ -87,6 +87,7 @@ def lib():
         L.flow2d_compute_device.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params)]
         L.flow2d_compute_async.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Params)]
         L.flow2d_synchronize.argtypes = [vp]
+        L.flow2d_prepare.argtypes = [vp, C.POINTER(Params)]
         L.flow2d_last_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_int), fp]
         L.flow2d_last_launch_counts.argtypes = [vp, C.POINTER(C.c_longlong)]
         L.flow2d_graph_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
@@ -274,6 +275,10 @@ class Flow2D:
 
     def synchronize(self):
         self._check(lib().flow2d_synchronize(self._h))
+
+    def prepare(self, params):
+        """flow2d_prepare: capture the schedule of compute / compute_async for these parameters now."""
+        self._check(lib().flow2d_prepare(self._h, C.byref(params)))
 
     def compute_device(self, d_f0, d_f1, d_u, d_v, params):
         self._check(lib().flow2d_compute_device(self._h, _ptr(d_f0), _ptr(d_f1), _ptr(d_u), _ptr(d_v), C.byref(params)))

@@ -1039,8 +1039,9 @@ struct GraphKey {
   const void* timing;
 };
 
+// launch = false: only make sure the schedule is in the graph cache (flow2d_prepare)
 int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame_1, float* out_u, float* out_v,
-                      const flow2d_params* p) {
+                      const flow2d_params* p, bool launch = true) {
   int median = 1;
   TRY(validate_params(h, p, &median));
   if (p->gaussian_sigma > 0.0f) {
@@ -1050,7 +1051,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   TRY(ensure_ext(h, p));  // allocations of the opt-in extensions: never inside a stream capture
   static const bool no_graph = std::getenv("FLOW2D_NO_GRAPH") != nullptr;  // A/B switch for measurements
   // per-level timers are CUDA events between the stages: plain enqueue (the reference's timed path is not a graph either)
-  if (no_graph || p->report_level_times) return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+  if (no_graph || p->report_level_times) return launch ? enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p) : FLOW2D_OK;
 
   GraphKey key;
   std::memset(&key, 0, sizeof key);
@@ -1072,6 +1073,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   flow2d_handle::GraphEntry* slot = nullptr;
   for (auto& g : h->graphs)
     if (g.exec && std::memcmp(&key, g.key, sizeof key) == 0) slot = &g;
+  if (slot && !launch) return FLOW2D_OK;
   if (slot) {
     NvtxRange r_replay("flow2d: graph replay");
     CU_TRY(h, cudaGraphLaunch(slot->exec, h->stream));
@@ -1087,7 +1089,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   }
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     (void)cudaGetLastError();
-    return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);  // e.g. the stream is already capturing
+    return launch ? enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p) : FLOW2D_OK;  // e.g. the stream is already capturing
   }
   reset_launch_counts(h);
   const int rc = enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
@@ -1097,13 +1099,13 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
     (void)cudaGetLastError();
     if (graph) cudaGraphDestroy(graph);
     if (rc != FLOW2D_OK) return rc;
-    return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+    return launch ? enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p) : FLOW2D_OK;
   }
   cudaGraphExec_t exec = nullptr;
   if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
     (void)cudaGetLastError();
     cudaGraphDestroy(graph);
-    return enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p);
+    return launch ? enqueue_pyramid(h, frame_0, frame_1, out_u, out_v, p) : FLOW2D_OK;
   }
   cudaGraphDestroy(graph);
   // a free slot, else the least recently used one (its graph may still be executing: destroying an exec that is
@@ -1124,7 +1126,7 @@ int compute_on_device(flow2d_handle* h, const float* frame_0, const float* frame
   slot->iter_levels = h->iter_levels; slot->iter_default = h->iter_default;
   slot->last_use = ++h->graph_clock;
   ++h->graph_captures;
-  CU_TRY(h, cudaGraphLaunch(slot->exec, h->stream));
+  if (launch) CU_TRY(h, cudaGraphLaunch(slot->exec, h->stream));
   return FLOW2D_OK;
 }
 
@@ -1448,6 +1450,12 @@ int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* fr
   CU_TRY(h, cudaMemcpy2DAsync(flow_v, row, out_v, dpitch, row, h->H, cudaMemcpyDeviceToHost, st));
   CU_TRY(h, cudaEventRecord(h->ev_stop, st));
   return FLOW2D_OK;
+}
+
+int flow2d_prepare(flow2d_handle* h, const flow2d_params* p) {
+  if (!h || !p) return FLOW2D_ERR_INVALID_ARGUMENT;
+  CU_TRY(h, cudaSetDevice(h->device));
+  return compute_on_device(h, h->c[C_IN0], h->c[C_IN1], h->c[C_OUT_U], h->c[C_OUT_V], p, false);
 }
 
 int flow2d_synchronize(flow2d_handle* h) {

@@ -163,6 +163,18 @@ int Run(FrameSource& source, const std::string& out_prefix, const Options& opt, 
       return 1;
     }
 
+  // the first call of a handle captures its schedule into a CUDA graph (tens of milliseconds of host time): with K
+  // handles on each of N GPUs that is done here, from one host thread per GPU, instead of T times in a row by the
+  // scheduler while the GPUs wait
+  {
+    std::vector<std::thread> prep;
+    for (int d = 0; d < N; d++)
+      prep.emplace_back([&, d]() {
+        for (int k = d; k < T; k += N) flow2d_prepare(handles[k], &p);
+      });
+    for (auto& t : prep) t.join();
+  }
+
   std::vector<std::unique_ptr<Data2D>> frames, out_u, out_v;
   for (int i = 0; i < R; i++) frames.emplace_back(new Data2D(width, height));
   for (int i = 0; i < M; i++) {

@@ -145,6 +145,11 @@ FLOW2D_API int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, c
 FLOW2D_API int flow2d_compute_async(flow2d_handle* h, const float* frame_0, const float* frame_1,
                          float* flow_u, float* flow_v, const flow2d_params* p);
 FLOW2D_API int flow2d_synchronize(flow2d_handle* h);
+/* Optional: captures the schedule that flow2d_compute / flow2d_compute_async will replay for these parameters now (tens of
+ * milliseconds of host time for a full pyramid) instead of inside the first call.  Handles are independent: a program that
+ * owns many of them (K per GPU on N GPUs) prepares them from several host threads at once.  No reference counterpart (the
+ * reference JIT-compiles its PTX in Initialize, optical_flow_2d.cpp:59-82). */
+FLOW2D_API int flow2d_prepare(flow2d_handle* h, const flow2d_params* p);
 
 /* Diagnostics of the last flow2d_compute*(): kernels launched, pyramid levels run, and (after
  * flow2d_compute only) the device time in ms between the first H2D and the last D2H -- the span

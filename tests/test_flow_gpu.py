@@ -180,3 +180,18 @@ def test_zero_epsilon_is_exact(pkg, oracle, synth, torch_, es, ed):
     ou, ov = oracle.compute_flow(f0, f1, oracle.make_params(**cfg))
     same = (u == ou) | (np.isnan(u) & np.isnan(ou))
     assert same.all() and ((v == ov) | (np.isnan(v) & np.isnan(ov))).all()
+
+
+def test_prepare_captures_the_schedule_ahead(pkg, oracle, synth, torch_):
+    """flow2d_prepare: the graph of the host-API path is captured before the first call, which then only replays."""
+    w, h = 200, 150
+    f0, f1, _, _ = synth.make_pair(w, h, 4, U1=1.0)
+    cfg = dict(levels=50, scale=0.8, outer=3, inner=5)
+    fl = pkg.Flow2D(w, h)
+    p = pkg.default_params(**cfg)
+    fl.prepare(p)
+    assert fl.graph_stats() == (1, 0)
+    u, v = fl.compute(f0, f1, p)
+    assert fl.graph_stats() == (1, 1)
+    ou, ov = oracle.compute_flow(f0, f1, oracle.make_params(**cfg))
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
