@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 GREY, GRADIENT = 0, 1
-KERNEL_KINDS = 13  # FLOW2D_KERNEL_KINDS
+KERNEL_KINDS = 14  # FLOW2D_KERNEL_KINDS
 JACOBI, RED_BLACK = 0, 1  # FLOW2D_SCHEME_*
 TERM_DEFAULT, TERM_GRADIENT, TERM_LOG_GRADIENT, TERM_COMBINED = 0, 1, 2, 3  # FLOW2D_TERM_*
 MAX_LEVELS = 256   # FLOW2D_MAX_LEVELS

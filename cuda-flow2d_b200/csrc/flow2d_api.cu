@@ -19,6 +19,7 @@
 
 #include "../../include/flow2d.h"
 #include "kernels.h"
+#include "solve_cluster_geom.h"
 
 using namespace flow2d;
 
@@ -83,6 +84,12 @@ struct flow2d_handle {
   long long graph_captures = 0, graph_replays = 0;
   int sm_count = 148;
   bool pass3 = false;             // the TMA-staged persistent pass (solve_pass3.cu) is usable on this device / driver
+  // thread-block clusters for mid-size levels (solve_cluster.cu).  cluster_active[i][j]: clusters of 2^(i+1) CTAs x
+  // (256 << j) threads the device holds at once (0 = not launchable here)
+  int cluster_whole = 0;          // whole-level mode: FLOW2D_CLUSTER = 0 / 1 (unset: kClusterWholeDefault)
+  int cluster_pass = 0;           // pass mode: FLOW2D_CLUSTER_PASS = 0 / 1 (2-4: forced, see run_solve; unset: kClusterPassDefault)
+  bool cluster_compact = false;   // FLOW2D_CLUSTER_COMPACT: fewest CTAs instead of shortest sweeps
+  int cluster_active[4][3] = {};
   // opt-in extensions (flow2d_params.scheme / omega / data_term / residual_tolerance / cascaded_restriction); allocated on first use
   float* ext_pool = nullptr;      // six tensor planes of the extension data terms
   float* J6[6] = {};
@@ -138,7 +145,7 @@ int fail(flow2d_handle* h, int code, const char* fmt, ...) {
 
 const char* const kKindNames[FLOW2D_KERNEL_KINDS] = {"blur", "resample", "warp", "derivatives", "grad_tensor", "solve_pass",
                                                       "solve_pass(resident)", "solve_small_pass", "solve_tiny", "add_median",
-                                                      "add", "residual", "solve_ext"};
+                                                      "add", "residual", "solve_ext", "solve_cluster"};
 
 int check_launch(flow2d_handle* h, int kind, int kernels) {
   cudaError_t e = cudaGetLastError();
@@ -538,6 +545,56 @@ int run_solve_ext(flow2d_handle* h, const LevelGeom& g, const float* u, const fl
   return FLOW2D_OK;
 }
 
+// ---- thread-block clusters for mid-size levels (solve_cluster.cu) ---------------------------------------------------
+// Defaults of the two modes; FLOW2D_CLUSTER / FLOW2D_CLUSTER_PASS override them per handle (A/B measurements, tests).
+constexpr int kClusterWholeDefault = 0;
+constexpr int kClusterPassDefault = 0;
+
+// Time of one barrier-to-barrier phase of the cluster kernel in us (a sweep, or one of the three set-up phases of an
+// outer iteration) by threads per CTA: issue time of the CTA's warps + the cluster barrier.
+double cluster_phase_us(int threads) { return threads <= 256 ? 0.27 : threads <= 512 ? 0.33 : 0.45; }
+
+struct ClusterPlan {
+  ClusterGeom cg;
+  int threads = 0;   // 0 = no cluster shape fits
+  int active = 0;    // clusters of that shape the device holds at once
+  double phase_us = 0.0;
+};
+
+// The cluster shape for a region of rw x rh cells: cx * cy in {2, 4, 8, 16} CTAs with blocks of ceil(rw / cx) x
+// ceil(rh / cy) >= 8 x 8 cells, at most 1024 per CTA.  Fewer threads per CTA make shorter sweeps (the CTA's warps issue
+// one after the other), more CTAs occupy more SMs: `compact` weighs the second, the default the first.
+ClusterPlan plan_cluster(const int (*cluster_active)[3], int rw, int rh, bool compact) {
+  ClusterPlan best;
+  double best_cost = 1e300;
+  for (int i = 0; i < 4; i++) {
+    const int csize = 2 << i;
+    for (int cx = 1; cx <= csize; cx *= 2) {
+      const int cy = csize / cx;
+      int tw = (rw + cx - 1) / cx, th = (rh + cy - 1) / cy;
+      if (tw < kClusterMinBlock) tw = kClusterMinBlock;
+      if (th < kClusterMinBlock) th = kClusterMinBlock;
+      const int cells = tw * th;
+      if (cells > 1024) continue;
+      const int j = cells <= 256 ? 0 : cells <= 512 ? 1 : 2;
+      const int active = cluster_active[i][j];
+      if (active <= 0) continue;
+      const double phase = cluster_phase_us(256 << j);
+      // tie-breakers: little padding (cells beyond the region), squarish blocks (fewer edge cells to push)
+      const double cost = phase * (1.0 + (compact ? 0.3 : 0.02) * csize) + 1e-6 * ((double)cells * csize - (double)rw * rh) +
+                          1e-5 * (tw + th);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.cg.cx = cx; best.cg.cy = cy; best.cg.tw = tw; best.cg.th = th; best.cg.ncx = 1;
+        best.threads = 256 << j;
+        best.active = active;
+        best.phase_us = phase;
+      }
+    }
+  }
+  return best;
+}
+
 // CudaOperationSolve2D::Execute (cuda_operation_solve_2d.cpp:229-299) on top of the solve kernels.
 // The result is left in du_a/dv_a; du_b/dv_b are scratch.  fx,fy,ft (and J in gradient mode) must
 // hold the derivative planes of this level (on the own rows +- plan.in_margin when the level is slabbed).
@@ -584,6 +641,23 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
     a.sweeps = inner; a.outer = outer;
     launch_solve_tiny(h->stream, a, grad);
     return check_launch(h, FLOW2D_K_SOLVE_TINY, 1);
+  }
+  // mid-size levels (up to 16 x 1024 pixels): one thread-block cluster, one thread per pixel, halos through distributed
+  // shared memory, all outer iterations in the kernel
+  if (h->cluster_whole && !slabbed && !early && p->resident_levels == 0 && g.w >= 2 && g.h >= 2 &&
+      (long long)g.w * g.h <= (long long)kClusterMaxCtas * 1024) {
+    const ClusterPlan cp = plan_cluster(h->cluster_active, g.w, g.h, h->cluster_compact || p->throughput_mode != 0);
+    if (cp.threads) {
+      a.du_in = a.dv_in = nullptr;
+      a.phi_in = a.ksi_in = nullptr;
+      a.du_out = du_a; a.dv_out = dv_a;
+      a.phi_out = want_phi ? phi : nullptr; a.ksi_out = want_phi ? ksi : nullptr;
+      a.sweeps = inner; a.outer = outer;
+      a.ow = cp.cg.cx * cp.cg.tw; a.oh = cp.cg.cy * cp.cg.th; a.halo_x = a.halo_y = 0;
+      a.pdl = 0;
+      launch_solve_cluster(h->stream, a, grad, cp.cg, cp.threads, 1);
+      return check_launch(h, FLOW2D_K_SOLVE_CLUSTER, 1);
+    }
   }
   // resident mode: the whole level (plus a one-cell apron) fits one CTA's region
   const bool fits = g.w + 4 + 1 <= kSolveLW && g.h + 1 + 1 <= kSolveLH;
@@ -687,7 +761,34 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
           const double t = 1.0 + (double)((n + sms - 1) / sms) * (2.5 + 1.6 * (ts * ts) / 1024.0);
           if (t < t_best) { t_best = t; ts_best = ts; }
         }
-        if (ts_best) {
+        // the same pass on a grid of clusters (FLOW2D_CLUSTER_PASS): 128x128 (16 x 1024 threads) or 128x64 (16 x 512)
+        // regions with the S+1 halo, 82 % / 74 % of the cells are results instead of 39 % of a 32x32 region
+        ClusterPlan cp_best;
+        int cl_n = 0;
+        if (h->cluster_pass && !slabbed) {
+          // FLOW2D_CLUSTER_PASS: 1 = where the model says so, 2 = always (shape by the model), 3 / 4 = always 128x64 / 128x128
+          static const int kShape[2][2] = {{128, 64}, {128, 128}};
+          double t_cl = 1e300;
+          for (int k = 0; k < 2; ++k) {
+            if ((h->cluster_pass == 3 && k != 0) || (h->cluster_pass == 4 && k != 1)) continue;
+            const int cw = kShape[k][0] - 2 * (s + 1), ch = kShape[k][1] - 2 * (s + 1);
+            const ClusterPlan cp = plan_cluster(h->cluster_active, kShape[k][0], kShape[k][1], false);
+            if (!cp.threads || cp.cg.cx * cp.cg.tw != kShape[k][0] || cp.cg.cy * cp.cg.th != kShape[k][1]) continue;
+            const long long n = (long long)((g.w + cw - 1) / cw) * ((vb - va + ch - 1) / ch);
+            const double t = 1.0 + (double)((n + cp.active - 1) / cp.active) * (1.3 + (3 + s) * cp.phase_us);
+            if (t < t_cl) { t_cl = t; cp_best = cp; cl_n = (int)n; }
+          }
+          if (cl_n && h->cluster_pass == 1 && !(t_cl < t_best)) cl_n = 0;
+        }
+        if (cl_n) {
+          small = true;
+          a.halo_x = a.halo_y = s + 1;
+          a.ow = cp_best.cg.cx * cp_best.cg.tw - 2 * (s + 1);
+          a.oh = cp_best.cg.cy * cp_best.cg.th - 2 * (s + 1);
+          cp_best.cg.ncx = (g.w + a.ow - 1) / a.ow;
+          launch_solve_cluster(h->stream, a, grad, cp_best.cg, cp_best.threads, cl_n);
+          TRY(check_launch(h, FLOW2D_K_SOLVE_CLUSTER, 1));
+        } else if (ts_best) {
           small = true;
           const int so = ts_best - 2 * (s + 1);
           a.halo_x = a.halo_y = s + 1;
@@ -1262,6 +1363,19 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
   }
   h->stream = h->own_stream;
   h->pass3 = solve_pass3_available();
+  {
+    // A/B switches, read per handle (tests flip them between handles of one process)
+    const char* e = std::getenv("FLOW2D_CLUSTER");
+    h->cluster_whole = e ? (std::atoi(e) != 0) : kClusterWholeDefault;
+    e = std::getenv("FLOW2D_CLUSTER_PASS");
+    h->cluster_pass = e ? std::atoi(e) : kClusterPassDefault;
+    h->cluster_compact = std::getenv("FLOW2D_CLUSTER_COMPACT") != nullptr;
+    int cmax = kClusterMaxCtas;
+    if ((e = std::getenv("FLOW2D_CLUSTER_MAX")) != nullptr) cmax = std::atoi(e);
+    if (h->cluster_whole || h->cluster_pass)
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 3; j++) h->cluster_active[i][j] = (2 << i) <= cmax ? solve_cluster_max_active(2 << i, 256 << j) : 0;
+  }
   *out = h;
   return FLOW2D_OK;
 }
@@ -1401,6 +1515,33 @@ int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts) {
   for (int k = 0; k < FLOW2D_KERNEL_KINDS; k++) counts[k] = h->kind_launches[k];
   return FLOW2D_OK;
 }
+int flow2d_cluster_shape(int rw, int rh, int compact, int shape[5]) {
+  if (!shape || rw < 2 || rh < 2) return FLOW2D_ERR_INVALID_ARGUMENT;
+  int all[4][3];
+  for (auto& row : all)
+    for (int& v : row) v = 1;
+  const ClusterPlan cp = plan_cluster(all, rw, rh, compact != 0);
+  if (!cp.threads) return FLOW2D_ERR_UNSUPPORTED;
+  shape[0] = cp.cg.cx; shape[1] = cp.cg.cy; shape[2] = cp.cg.tw; shape[3] = cp.cg.th; shape[4] = cp.threads;
+  return FLOW2D_OK;
+}
+
+int flow2d_debug_cluster_cell(const int geom[5], const int level[7], int rank, int cluster, int thread, int cell[15]) {
+  if (!geom || !level || !cell) return FLOW2D_ERR_INVALID_ARGUMENT;
+  ClusterGeom cg;
+  cg.cx = geom[0]; cg.cy = geom[1]; cg.tw = geom[2]; cg.th = geom[3]; cg.ncx = geom[4];
+  if (cg.cx < 1 || cg.cy < 1 || cg.cx * cg.cy > kClusterMaxCtas || cg.tw < 2 || cg.th < 2 || cg.tw * cg.th > 1024 || cg.ncx < 1 ||
+      rank < 0 || rank >= cg.cx * cg.cy || cluster < 0 || thread < 0 || thread >= 1024)
+    return FLOW2D_ERR_INVALID_ARGUMENT;
+  ClusterLevel lv;
+  lv.w = level[0]; lv.h = level[1]; lv.ow = level[2]; lv.oh = level[3]; lv.halo = level[4]; lv.y0 = level[5]; lv.y1 = level[6];
+  const ClusterCell c = cluster_cell(cg, lv, rank, cluster, thread);
+  const int v[15] = {c.ac, c.al, c.ar, c.au, c.ad, c.push_h_rank, c.push_h, c.push_v_rank, c.push_v, c.gx, c.gy, c.mine, c.live, c.out,
+                     cluster_plane(cg.tw * cg.th <= 256 ? 256 : cg.tw * cg.th <= 512 ? 512 : 1024)};
+  for (int i = 0; i < 15; i++) cell[i] = v[i];
+  return FLOW2D_OK;
+}
+
 const char* flow2d_kernel_kind_name(int kind) { return kind >= 0 && kind < FLOW2D_KERNEL_KINDS ? kKindNames[kind] : ""; }
 
 int flow2d_compute_device(flow2d_handle* h, const float* d_frame_0, const float* d_frame_1, float* d_flow_u,
@@ -1550,7 +1691,7 @@ int flow2d_slab_connect(flow2d_handle* h, int rank, int world, void* mailbox_abo
   if (world > 1) {
     // a rank's stream spins on flags its neighbours set: no kernel may be loaded lazily (with a context
     // synchronisation) once the ranks are in flight
-    preload_pyramid_kernels(); preload_median_kernels(); preload_solve_kernels(); preload_solve_pass2_kernels(); preload_solve_pass3_kernels();
+    preload_pyramid_kernels(); preload_median_kernels(); preload_solve_kernels(); preload_solve_pass2_kernels(); preload_solve_pass3_kernels(); preload_solve_cluster_kernels();
     preload_slab_kernels();
     (void)cudaGetLastError();
   }

@@ -86,6 +86,23 @@ void launch_solve_small_pass(cudaStream_t st, const SolveArgs& a, bool grad, int
 bool solve_tiny_fits(int w, int h);
 void launch_solve_tiny(cudaStream_t st, const SolveArgs& a, bool grad);
 
+// ---- solve_cluster.cu: a mid-size level on one thread-block cluster (one thread per pixel, halos through distributed
+// shared memory, barrier.cluster per sweep) ----
+constexpr int kClusterMaxCtas = 16;   // 8 is the portable cluster size; 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed
+constexpr int kClusterMinBlock = 8;   // a CTA's block is at least 8 x 8 cells (bounds its shared planes, see cluster_plane)
+struct ClusterGeom {
+  int cx, cy;   // CTAs of a cluster in x and y: launched as (cx * cy, 1, 1), rank r at (r % cx, r / cx)
+  int tw, th;   // block of one CTA, tw * th <= threads, both >= kClusterMinBlock
+  int ncx;      // regions per row of the level (pass mode); 1 = the region covers the level
+};
+// whole level: a.outer / a.sweeps = all iterations, a.ow = cx * tw, a.oh = cy * th, a.halo_x = a.halo_y = 0, clusters = 1
+// pass: a.outer = 1, a.halo_x = a.halo_y = a.sweeps + 1, a.ow = cx * tw - 2 * halo, a.oh = cy * th - 2 * halo,
+//       clusters = ncx * region rows.  threads = 256, 512 or 1024.
+void launch_solve_cluster(cudaStream_t st, const SolveArgs& a, bool grad, const ClusterGeom& cg, int threads, int clusters);
+// clusters of `csize` CTAs x `threads` threads the device holds at once; 0 = that shape cannot be launched here
+int solve_cluster_max_active(int csize, int threads);
+void preload_solve_cluster_kernels();
+
 // ---- slab.cu: halo exchange between neighbour GPUs through peer-mapped mailboxes ----
 struct SlabPushDir {
   float* dst[2];                // receive buffers of the two fields in the neighbour's mailbox (peer mapping)

@@ -41,6 +41,7 @@
 
 #include "kernels.h"
 #include "solve_common.cuh"
+#include "solve_onepx.cuh"
 
 namespace flow2d {
 
@@ -527,162 +528,7 @@ void launch_solve_pass(cudaStream_t st, const SolveArgs& a, bool grad, int grid_
 // ---------------------------------------------------------------------------------------------
 constexpr int kTinyMax = 1024;
 
-__device__ __forceinline__ float div_rn1(float a, float d, float r) {
-  const float q0 = a * r;
-  float q = fmaf(r, fmaf(-d, q0, a), q0);
-  if (!(r != 0.f && in_fast_range(a))) q = (a == 0.f && r != 0.f) ? q0 : slow_div(a, d);
-  return q;
-}
-
-// ---- one pixel per thread: the part solve_tiny and solve_small_pass share -------------------------
-// Nine shared planes of N floats (N = pixels of the CTA); a thread keeps five 32-bit shared addresses
-// (its own cell and its four neighbours in plane 0) and reaches every plane with a compile-time byte
-// offset, so a neighbour read is one LDS without address arithmetic; the sweep loop is unrolled by the
-// parity of the exchange buffer.
-enum { Q_U = 0, Q_V, Q_DU, Q_DV, Q_PHI, Q_SU0, Q_SV0, Q_SU1, Q_SV1, kOnePxPlanes };
-
-template <int N, int PLANE>
-__device__ __forceinline__ float ldq(unsigned addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1 + %2];" : "=f"(v) : "r"(addr), "n"(PLANE * N * 4) : "memory");
-  return v;
-}
-template <int N, int PLANE>
-__device__ __forceinline__ void stq(unsigned addr, float v) {
-  asm volatile("st.shared.f32 [%0 + %1], %2;" ::"r"(addr), "n"(PLANE * N * 4), "f"(v) : "memory");
-}
-
-struct OnePx {
-  unsigned ac, al, ar, au, ad;           // shared addresses in plane 0: own cell, left, right, up, down
-  float uc, vc, fx, fy, ft;              // constants of the pixel
-  float J11, J22, nJ12, nJ13, nJ23;
-  float wxp, wxm, wyp, wym;              // alpha / h^2, zero across the image border
-  float hx2, hy2, rhx2, rhy2;
-  float e_smooth, e_data;
-  bool live;                             // false = the cell is inert (outside the image): zero weights, ksi = 0
-};
-
-// Division in the one-pixel kernels.  Fast variant: the hardware's fast-path sequence with the hoisted
-// reciprocal, WITHOUT a branch; whether every dividend was inside the range where that sequence equals
-// div.rn (or zero, which it also gets right) is accumulated in `ok` and checked once per outer iteration
-// by the whole CTA.  If anything was out of range -- practically never -- the caller repeats the outer
-// iteration with the EXACT variant (plain IEEE divisions).  A per-division branch costs ten control
-// instructions next to three arithmetic ones.
-template <bool EXACT>
-__device__ __forceinline__ float div1(float a, float d, float r, bool& ok) {
-  if (EXACT) return a / d;
-  const float q0 = a * r;
-  const float m = fabsf(a);
-  ok = ok && (m < 0x1p60f) && (m >= 0x1p-60f || m == 0.f);
-  return fmaf(r, fmaf(-d, q0, a), q0);
-}
-
-// sqrt.rn / rcp.rn the same way: the compiler's own fast-path sequences (MUFU.RSQ / MUFU.RCP + the Newton
-// step it emits for sqrtf and 1.f/x on sm_100) without their range branch; arguments outside 2^-100 .. 2^100
-// (inside the range where those sequences ARE sqrt.rn / rcp.rn) clear `ok`.  Arguments here are positive.
-template <bool EXACT>
-__device__ __forceinline__ float sqrt1(float x, bool& ok) {
-  if (EXACT) return sqrtf(x);
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  const float s = x * y, hh = y * 0.5f;
-  ok = ok && x >= 0x1p-100f && x < 0x1p100f;
-  return fmaf(fmaf(-s, s, x), hh, s);
-}
-template <bool EXACT>
-__device__ __forceinline__ float rcp1(float x, bool& ok) {
-  if (EXACT) return 1.f / x;
-  float r0;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(x));
-  const float e = -fmaf(x, r0, -1.f);
-  ok = ok && x >= 0x1p-100f && x < 0x1p100f;
-  return fmaf(r0, e, r0);
-}
-
-// One outer iteration: publish du, dv; phi, ksi; weights; `sweeps` Jacobi sweeps.  The caller has put uc, vc
-// into planes Q_U, Q_V.  Ends with a barrier.  Same operations, in the same order, as solve_pass.
-// Returns false (to every thread of the CTA alike) if the fast divisions were not safe somewhere.
-template <int N, bool EXACT>
-__device__ __forceinline__ bool one_px_outer_impl(const OnePx& c, int sweeps, float& du, float& dv, float& phi, float& ksi) {
-  bool ok = c.rhx2 != 0.f && c.rhy2 != 0.f;
-  stq<N, Q_DU>(c.ac, du);
-  stq<N, Q_DV>(c.ac, dv);
-  __syncthreads();
-  {
-    // solve_2d.cu:141-162
-    const float dux = div1<EXACT>(((ldq<N, Q_U>(c.ar) - ldq<N, Q_U>(c.al)) + ldq<N, Q_DU>(c.ar)) - ldq<N, Q_DU>(c.al), c.hx2, c.rhx2, ok);
-    const float duy = div1<EXACT>(((ldq<N, Q_U>(c.ad) - ldq<N, Q_U>(c.au)) + ldq<N, Q_DU>(c.ad)) - ldq<N, Q_DU>(c.au), c.hy2, c.rhy2, ok);
-    const float dvx = div1<EXACT>(((ldq<N, Q_V>(c.ar) - ldq<N, Q_V>(c.al)) + ldq<N, Q_DV>(c.ar)) - ldq<N, Q_DV>(c.al), c.hx2, c.rhx2, ok);
-    const float dvy = div1<EXACT>(((ldq<N, Q_V>(c.ad) - ldq<N, Q_V>(c.au)) + ldq<N, Q_DV>(c.ad)) - ldq<N, Q_DV>(c.au), c.hy2, c.rhy2, ok);
-    float s = duy * duy;
-    s = fmaf(dux, dux, s);
-    s = fmaf(dvx, dvx, s);
-    s = fmaf(dvy, dvy, s);
-    s = fmaf(c.e_smooth, c.e_smooth, s);
-    const float rr = sqrt1<EXACT>(s, ok);
-    phi = rcp1<EXACT>(rr + rr, ok);
-    // solve_2d.cu:176-196: always the brightness tensor
-    const float j11 = c.fx * c.fx, j22 = c.fy * c.fy, j12 = c.fx * c.fy, j13 = c.fx * c.ft, j23 = c.fy * c.ft;
-    const float ta = j13 + fmaf(j11, du, j12 * dv);
-    const float tb = j23 + fmaf(j12, du, j22 * dv);
-    const float tc = fmaf(c.ft, c.ft, fmaf(j13, du, j23 * dv));
-    float sq = fmaf(du, ta, dv * tb) + tc;
-    sq = sq * ((sq > 0.f) ? 1.f : 0.f);
-    const float q = sqrt1<EXACT>(fmaf(c.e_data, c.e_data, sq), ok);
-    const float rq = rcp1<EXACT>(q + q, ok);
-    ksi = c.live ? rq : 0.f;
-  }
-  stq<N, Q_PHI>(c.ac, phi);
-  __syncthreads();
-  // solve_2d.cu:333-349, 363, 367; cells outside the image are inert
-  float axp = c.wxp * ((ldq<N, Q_PHI>(c.ar) + phi) * 0.5f);
-  float axm = c.wxm * ((ldq<N, Q_PHI>(c.al) + phi) * 0.5f);
-  float ayp = c.wyp * ((ldq<N, Q_PHI>(c.ad) + phi) * 0.5f);
-  float aym = c.wym * ((ldq<N, Q_PHI>(c.au) + phi) * 0.5f);
-  const float sumH = ((axp + axm) + ayp) + aym;
-  float denU = fmaf(c.J11, ksi, sumH), denV = fmaf(c.J22, ksi, sumH);
-  if (!c.live) { axp = axm = ayp = aym = 0.f; denU = denV = 1.f; }
-  const float rU = EXACT ? 0.f : fast_path_rcp(denU), rV = EXACT ? 0.f : fast_path_rcp(denV);
-  ok = ok && (EXACT || (rU != 0.f && rV != 0.f));
-  const float uc = c.uc, vc = c.vc;
-  stq<N, Q_SU0>(c.ac, uc + du);
-  stq<N, Q_SV0>(c.ac, vc + dv);
-  __syncthreads();
-  // solve_2d.cu:350-367 as compiled: mul, then fma chain xm, xp, yp, ym
-  auto sweep = [&](auto even) {
-    constexpr bool EVEN = decltype(even)::value;  // sweep 0, 2, ...: reads buffer 0, writes buffer 1
-    constexpr int CU = EVEN ? Q_SU0 : Q_SU1, CV = EVEN ? Q_SV0 : Q_SV1, NU = EVEN ? Q_SU1 : Q_SU0, NV = EVEN ? Q_SV1 : Q_SV0;
-    float sumU = axm * (ldq<N, CU>(c.al) - uc);
-    sumU = fmaf(axp, ldq<N, CU>(c.ar) - uc, sumU);
-    sumU = fmaf(ayp, ldq<N, CU>(c.ad) - uc, sumU);
-    sumU = fmaf(aym, ldq<N, CU>(c.au) - uc, sumU);
-    float sumV = axm * (ldq<N, CV>(c.al) - vc);
-    sumV = fmaf(axp, ldq<N, CV>(c.ar) - vc, sumV);
-    sumV = fmaf(ayp, ldq<N, CV>(c.ad) - vc, sumV);
-    sumV = fmaf(aym, ldq<N, CV>(c.au) - vc, sumV);
-    du = div1<EXACT>(fmaf(ksi, fmaf(c.nJ12, dv, c.nJ13), sumU), denU, rU, ok);
-    dv = div1<EXACT>(fmaf(ksi, fmaf(c.nJ12, du, c.nJ23), sumV), denV, rV, ok);
-    stq<N, NU>(c.ac, uc + du);
-    stq<N, NV>(c.ac, vc + dv);
-    __syncthreads();
-  };
-  for (int k = 0; k < sweeps; k += 2) {
-    sweep(std::true_type{});
-    if (k + 1 < sweeps) sweep(std::false_type{});
-  }
-  if (EXACT) return true;
-  return __syncthreads_or(c.live && !ok) == 0;  // what an inert cell (outside the image) computes is never used
-}
-
-template <int N>
-__device__ __forceinline__ void one_px_outer(const OnePx& c, int sweeps, bool exact, float& du, float& dv, float& phi, float& ksi) {
-  const float du0 = du, dv0 = dv;
-  if (exact || !one_px_outer_impl<N, false>(c, sweeps, du, dv, phi, ksi)) {
-    du = du0;
-    dv = dv0;
-    one_px_outer_impl<N, true>(c, sweeps, du, dv, phi, ksi);
-  }
-}
+// (div1 / sqrt1 / rcp1, the nine shared planes and one_px_outer live in solve_onepx.cuh: solve_cluster.cu shares them)
 
 template <bool GRAD>
 __global__ void __launch_bounds__(kTinyMax, 1) solve_tiny_kernel(const SolveArgs a) {

@@ -163,10 +163,23 @@ enum {
   FLOW2D_K_SOLVE_RESIDENT, FLOW2D_K_SOLVE_SMALL_PASS, FLOW2D_K_SOLVE_TINY, FLOW2D_K_ADD_MEDIAN, FLOW2D_K_ADD,
   FLOW2D_K_RESIDUAL,
   FLOW2D_K_EXT,  /* the kernels of the opt-in extensions (csrc/solve_ext.cu) */
+  FLOW2D_K_SOLVE_CLUSTER,  /* a mid-size level solved on one thread-block cluster (csrc/solve_cluster.cu) */
   FLOW2D_KERNEL_KINDS
 };
 FLOW2D_API int flow2d_last_launch_counts(const flow2d_handle* h, long long* counts /* [FLOW2D_KERNEL_KINDS] */);
 FLOW2D_API const char* flow2d_kernel_kind_name(int kind);
+
+/* ---- scheduler introspection (used by the CPU tests; no reference counterpart) ------------------------------------
+ * Mid-size levels are solved on one thread-block cluster (csrc/solve_cluster.cu): cx * cy CTAs with a tw x th block of
+ * the level each, one thread per pixel.  flow2d_cluster_shape: the decomposition the scheduler picks for a region of
+ * rw x rh cells when every cluster shape is launchable, shape = {cx, cy, tw, th, threads per CTA}; `compact` != 0 weighs
+ * occupied SMs over sweep latency (throughput_mode).  FLOW2D_ERR_UNSUPPORTED = the region does not fit a cluster.
+ * flow2d_debug_cluster_cell: what one thread of that kernel works on, computed by the very function the kernel calls
+ * (csrc/solve_cluster_geom.h) -- geom = {cx, cy, tw, th, regions per row}, level = {w, h, ow, oh, halo, y0, y1},
+ * cell = {own, left, right, up, down offsets in a shared plane, push rank / offset (horizontal), push rank / offset
+ * (vertical), gx, gy, has a cell, live, output, floats per shared plane}. */
+FLOW2D_API int flow2d_cluster_shape(int rw, int rh, int compact, int shape[5]);
+FLOW2D_API int flow2d_debug_cluster_cell(const int geom[5], const int level[7], int rank, int cluster, int thread, int cell[15]);
 
 /* The level schedule of one (containers, parameters) combination is captured into a CUDA graph on first use and replayed
  * afterwards; a handle keeps the 8 most recently used graphs, so a caller that rotates a few containers (a frame ring)
