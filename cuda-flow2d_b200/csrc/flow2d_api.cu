@@ -86,7 +86,8 @@ struct flow2d_handle {
   bool pass3 = false;             // the TMA-staged persistent pass (solve_pass3.cu) is usable on this device / driver
   // thread-block clusters for mid-size levels (solve_cluster.cu).  cluster_active[i][j]: clusters of 2^(i+1) CTAs x
   // (256 << j) threads the device holds at once (0 = not launchable here)
-  int cluster_whole = 0;          // whole-level mode: FLOW2D_CLUSTER = 0 / 1 (unset: kClusterWholeDefault)
+  int cluster_whole = 0;          // whole-level mode: FLOW2D_CLUSTER = 0 off / 1 levels whose blocks fit 256 threads per CTA
+                                  // (<= 4096 px) / 2 every level that fits a cluster (<= 16384 px); unset: kClusterWholeDefault
   int cluster_pass = 0;           // pass mode: FLOW2D_CLUSTER_PASS = 0 / 1 (2-4: forced, see run_solve; unset: kClusterPassDefault)
   bool cluster_compact = false;   // FLOW2D_CLUSTER_COMPACT: fewest CTAs instead of shortest sweeps
   int cluster_active[4][3] = {};
@@ -547,16 +548,25 @@ int run_solve_ext(flow2d_handle* h, const LevelGeom& g, const float* u, const fl
 
 // ---- thread-block clusters for mid-size levels (solve_cluster.cu) ---------------------------------------------------
 // Defaults of the two modes; FLOW2D_CLUSTER / FLOW2D_CLUSTER_PASS override them per handle (A/B measurements, tests).
-constexpr int kClusterWholeDefault = 0;
+// Measured on B200 (profiles/r02/cluster_ab/, one level of the 1024^2 pyramid = 40 x 5 iterations):
+//   blocks of <= 256 threads (levels of 1 025 .. 4 096 px)  138-154 us against 142-151 us with one solve_small_pass launch per
+//       outer iteration: the same latency on 16 small CTAs instead of 16-36 CTAs of 576 threads -> on by default
+//   512 threads (.. 8 192 px) 188-193 us against 146 us, 1024 threads (.. 16 384 px) 252-262 us against 151-181 us: the
+//       barrier.cluster (MEMBAR.ALL.GPU + UCGABAR + CCTL.IVALL, ~0.3 us with 16 CTAs) costs more per sweep than the relaunch
+//       costs per outer iteration.  With several pairs sharing the GPU the smaller SM footprint still wins (C4 batch +0.8 %
+//       device / +1.5 % end to end, C1b batch +2.2 % / +4 %) but one pair alone loses 5 % (C4) to 11 % (C1b): FLOW2D_CLUSTER=2
+//   pass mode: 1.5-3.3x slower than solve_small_pass / the tiled pass on every level -> off
+constexpr int kClusterWholeDefault = 1;
 constexpr int kClusterPassDefault = 0;
 
 // Time of one barrier-to-barrier phase of the cluster kernel in us (a sweep, or one of the three set-up phases of an
-// outer iteration) by threads per CTA: issue time of the CTA's warps + the cluster barrier.
-double cluster_phase_us(int threads) { return threads <= 256 ? 0.27 : threads <= 512 ? 0.33 : 0.45; }
+// outer iteration): the cluster barrier + the issue time of the CTA's warps.  Fitted to the measurements above
+// (8 / 16 / 32 warps per CTA: 0.43 / 0.59 / 0.80 us).
+double cluster_phase_us(int threads) { return 0.31 + 0.0155 * ((threads + 31) / 32); }
 
 struct ClusterPlan {
   ClusterGeom cg;
-  int threads = 0;   // 0 = no cluster shape fits
+  int threads = 0;   // threads per CTA (whole warps covering the block); 0 = no cluster shape fits
   int active = 0;    // clusters of that shape the device holds at once
   double phase_us = 0.0;
 };
@@ -579,14 +589,15 @@ ClusterPlan plan_cluster(const int (*cluster_active)[3], int rw, int rh, bool co
       const int j = cells <= 256 ? 0 : cells <= 512 ? 1 : 2;
       const int active = cluster_active[i][j];
       if (active <= 0) continue;
-      const double phase = cluster_phase_us(256 << j);
+      const int threads = (cells + 31) / 32 * 32;  // whole warps; the kernel's shared planes are sized by the bucket j
+      const double phase = cluster_phase_us(threads);
       // tie-breakers: little padding (cells beyond the region), squarish blocks (fewer edge cells to push)
       const double cost = phase * (1.0 + (compact ? 0.3 : 0.02) * csize) + 1e-6 * ((double)cells * csize - (double)rw * rh) +
                           1e-5 * (tw + th);
       if (cost < best_cost) {
         best_cost = cost;
         best.cg.cx = cx; best.cg.cy = cy; best.cg.tw = tw; best.cg.th = th; best.cg.ncx = 1;
-        best.threads = 256 << j;
+        best.threads = threads;
         best.active = active;
         best.phase_us = phase;
       }
@@ -647,7 +658,7 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   if (h->cluster_whole && !slabbed && !early && p->resident_levels == 0 && g.w >= 2 && g.h >= 2 &&
       (long long)g.w * g.h <= (long long)kClusterMaxCtas * 1024) {
     const ClusterPlan cp = plan_cluster(h->cluster_active, g.w, g.h, h->cluster_compact || p->throughput_mode != 0);
-    if (cp.threads) {
+    if (cp.threads && (cp.threads <= 256 || h->cluster_whole >= 2)) {
       a.du_in = a.dv_in = nullptr;
       a.phi_in = a.ksi_in = nullptr;
       a.du_out = du_a; a.dv_out = dv_a;
@@ -1366,7 +1377,7 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
   {
     // A/B switches, read per handle (tests flip them between handles of one process)
     const char* e = std::getenv("FLOW2D_CLUSTER");
-    h->cluster_whole = e ? (std::atoi(e) != 0) : kClusterWholeDefault;
+    h->cluster_whole = e ? std::atoi(e) : kClusterWholeDefault;
     e = std::getenv("FLOW2D_CLUSTER_PASS");
     h->cluster_pass = e ? std::atoi(e) : kClusterPassDefault;
     h->cluster_compact = std::getenv("FLOW2D_CLUSTER_COMPACT") != nullptr;

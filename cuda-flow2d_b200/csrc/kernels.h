@@ -97,7 +97,7 @@ struct ClusterGeom {
 };
 // whole level: a.outer / a.sweeps = all iterations, a.ow = cx * tw, a.oh = cy * th, a.halo_x = a.halo_y = 0, clusters = 1
 // pass: a.outer = 1, a.halo_x = a.halo_y = a.sweeps + 1, a.ow = cx * tw - 2 * halo, a.oh = cy * th - 2 * halo,
-//       clusters = ncx * region rows.  threads = 256, 512 or 1024.
+//       clusters = ncx * region rows.  threads: whole warps covering the block (tw * th <= threads <= 1024).
 void launch_solve_cluster(cudaStream_t st, const SolveArgs& a, bool grad, const ClusterGeom& cg, int threads, int clusters);
 // clusters of `csize` CTAs x `threads` threads the device holds at once; 0 = that shape cannot be launched here
 int solve_cluster_max_active(int csize, int threads);

@@ -131,7 +131,8 @@ int solve_cluster_max_active(int csize, int threads) {
   return total;
 }
 
-// clusters: regions of the level (1 in whole-level mode); cg.cx * cg.cy CTAs each, `threads` = 256, 512 or 1024
+// clusters: regions of the level (1 in whole-level mode); cg.cx * cg.cy CTAs each; `threads`: whole warps covering a block
+// (the instantiation, i.e. the size of the shared planes, follows from it: up to 256, 512 or 1024 cells)
 void launch_solve_cluster(cudaStream_t st, const SolveArgs& a, bool grad, const ClusterGeom& cg, int threads, int clusters) {
   const int csize = cg.cx * cg.cy;
   cudaLaunchConfig_t cfg = {};

@@ -172,7 +172,7 @@ FLOW2D_API const char* flow2d_kernel_kind_name(int kind);
 /* ---- scheduler introspection (used by the CPU tests; no reference counterpart) ------------------------------------
  * Mid-size levels are solved on one thread-block cluster (csrc/solve_cluster.cu): cx * cy CTAs with a tw x th block of
  * the level each, one thread per pixel.  flow2d_cluster_shape: the decomposition the scheduler picks for a region of
- * rw x rh cells when every cluster shape is launchable, shape = {cx, cy, tw, th, threads per CTA}; `compact` != 0 weighs
+ * rw x rh cells when every cluster shape is launchable, shape = {cx, cy, tw, th, threads per CTA (whole warps)}; `compact` != 0 weighs
  * occupied SMs over sweep latency (throughput_mode).  FLOW2D_ERR_UNSUPPORTED = the region does not fit a cluster.
  * flow2d_debug_cluster_cell: what one thread of that kernel works on, computed by the very function the kernel calls
  * (csrc/solve_cluster_geom.h) -- geom = {cx, cy, tw, th, regions per row}, level = {w, h, ow, oh, halo, y0, y1},

@@ -17,12 +17,14 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     "off": dict(FLOW2D_CLUSTER="0"),
-    "whole": dict(FLOW2D_CLUSTER="1"),
-    "whole_compact": dict(FLOW2D_CLUSTER="1", FLOW2D_CLUSTER_COMPACT="1"),
-    "whole_max8": dict(FLOW2D_CLUSTER="1", FLOW2D_CLUSTER_MAX="8"),
-    "whole_pass": dict(FLOW2D_CLUSTER="1", FLOW2D_CLUSTER_PASS="1"),
-    "whole_pass_forced": dict(FLOW2D_CLUSTER="1", FLOW2D_CLUSTER_PASS="2"),
+    "default": dict(),  # the cluster where a CTA's block fits 256 threads (levels of 1 025 .. 4 096 px)
+    "whole": dict(FLOW2D_CLUSTER="2"),  # every level that fits a cluster (.. 16 384 px)
+    "whole_compact": dict(FLOW2D_CLUSTER="2", FLOW2D_CLUSTER_COMPACT="1"),
+    "whole_max8": dict(FLOW2D_CLUSTER="2", FLOW2D_CLUSTER_MAX="8"),
+    "whole_pass": dict(FLOW2D_CLUSTER="2", FLOW2D_CLUSTER_PASS="1"),
+    "whole_pass_forced": dict(FLOW2D_CLUSTER="2", FLOW2D_CLUSTER_PASS="2"),
 }
+QUICK = ("off", "default", "whole", "off")  # `python tools/ab_cluster.py out.json quick`: the workloads only, these configurations
 KEYS = ("FLOW2D_CLUSTER", "FLOW2D_CLUSTER_PASS", "FLOW2D_CLUSTER_COMPACT", "FLOW2D_CLUSTER_MAX")
 
 
@@ -71,7 +73,8 @@ def main():
     import flow2d_loader
     m = flow2d_loader.load()
     import bench
-    out = {"levels_c4": level_times(torch, m, list(CONFIGS))}
+    quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
+    out = {"levels_c4": level_times(torch, m, ["off", "default"] if quick else list(CONFIGS))}
     for lv, r in out["levels_c4"].items():
         print(lv, {k: v["us"] for k, v in r.items()}, file=sys.stderr)
     if len(sys.argv) > 1:
@@ -82,7 +85,7 @@ def main():
     runs = [("c4_batch", "c4", 6, 3, 0, 0), ("c4_single", "c4", 10, 3, 1, 1), ("c1b_single", "c1b", 20, 3, 1, 1), ("c1b_batch", "c1b", 6, 3, 8, 16)]
     out["workloads"] = {}
     for label, key, steps, warmup, streams, pairs in runs:
-        for name in ("off", "whole", "whole_compact", "whole_pass", "off"):
+        for name in (QUICK if quick else ("off", "default", "whole", "whole_compact", "whole_pass", "off")):
             set_env(CONFIGS[name])
             try:
                 res, _ = bench.measure(ctx, key, steps, warmup, streams, pairs, detail=False)
