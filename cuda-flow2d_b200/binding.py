@@ -138,6 +138,12 @@ def default_params(**over):
     return p
 
 
+def live_handles(device=0):
+    """Handles of this process alive on `device` (flow2d_live_handles): with FLOW2D_CLUSTER unset, 4 or more switch the
+    mid-size levels to the thread-block-cluster solve."""
+    return int(lib().flow2d_live_handles(device))
+
+
 def max_warp_level(w, h, sf):
     return int(lib().flow2d_max_warp_level(w, h, sf))
 

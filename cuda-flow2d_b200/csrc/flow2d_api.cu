@@ -4,6 +4,7 @@
 // (src/optical_flow/optical_flow_2d.cpp:142-569) stage for stage, but everything is enqueued on one
 // stream without any host synchronisation inside the pyramid (the reference blocks on
 // cuStreamSynchronize after every inner sweep, cuda_operation_solve_2d.cpp:291).
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -86,8 +87,10 @@ struct flow2d_handle {
   bool pass3 = false;             // the TMA-staged persistent pass (solve_pass3.cu) is usable on this device / driver
   // thread-block clusters for mid-size levels (solve_cluster.cu).  cluster_active[i][j]: clusters of 2^(i+1) CTAs x
   // (256 << j) threads the device holds at once (0 = not launchable here)
-  int cluster_whole = 0;          // whole-level mode: FLOW2D_CLUSTER = 0 off / 1 levels whose blocks fit 256 threads per CTA
-                                  // (<= 4096 px) / 2 every level that fits a cluster (<= 16384 px); unset: kClusterWholeDefault
+  int cluster_whole = -1;         // whole-level mode: FLOW2D_CLUSTER = 0 off / 1 levels whose blocks fit 256 threads per CTA
+                                  // (<= 4096 px) / 2 every level that fits a cluster (<= 16384 px); unset = -1: by the number
+                                  // of handles alive on the device (cluster_mode below)
+  bool counted = false;           // this handle is included in g_live_handles
   int cluster_pass = 0;           // pass mode: FLOW2D_CLUSTER_PASS = 0 / 1 (2-4: forced, see run_solve; unset: kClusterPassDefault)
   bool cluster_compact = false;   // FLOW2D_CLUSTER_COMPACT: fewest CTAs instead of shortest sweeps
   int cluster_active[4][3] = {};
@@ -546,18 +549,34 @@ int run_solve_ext(flow2d_handle* h, const LevelGeom& g, const float* u, const fl
   return FLOW2D_OK;
 }
 
+// handles alive per device (this process): several handles on one GPU = several frame pairs in flight at once
+constexpr int kMaxCountedDevices = 64;
+std::atomic<int> g_live_handles[kMaxCountedDevices];
+int live_handles(int device) { return device >= 0 && device < kMaxCountedDevices ? g_live_handles[device].load() : 1; }
+
 // ---- thread-block clusters for mid-size levels (solve_cluster.cu) ---------------------------------------------------
 // Defaults of the two modes; FLOW2D_CLUSTER / FLOW2D_CLUSTER_PASS override them per handle (A/B measurements, tests).
-// Measured on B200 (profiles/r02/cluster_ab/, one level of the 1024^2 pyramid = 40 x 5 iterations):
+// Measured on B200 (profiles/r02/cluster_ab/, same box; one level of the 1024^2 pyramid = 40 x 5 iterations):
 //   blocks of <= 256 threads (levels of 1 025 .. 4 096 px)  138-154 us against 142-151 us with one solve_small_pass launch per
-//       outer iteration: the same latency on 16 small CTAs instead of 16-36 CTAs of 576 threads -> on by default
-//   512 threads (.. 8 192 px) 188-193 us against 146 us, 1024 threads (.. 16 384 px) 252-262 us against 151-181 us: the
-//       barrier.cluster (MEMBAR.ALL.GPU + UCGABAR + CCTL.IVALL, ~0.3 us with 16 CTAs) costs more per sweep than the relaunch
-//       costs per outer iteration.  With several pairs sharing the GPU the smaller SM footprint still wins (C4 batch +0.8 %
-//       device / +1.5 % end to end, C1b batch +2.2 % / +4 %) but one pair alone loses 5 % (C4) to 11 % (C1b): FLOW2D_CLUSTER=2
+//       outer iteration; 512 threads (.. 8 192 px) 188-193 us against 146 us; 1024 threads (.. 16 384 px) 252-262 us against
+//       151-181 us: the barrier.cluster (MEMBAR.ALL.GPU + UCGABAR + CCTL.IVALL, ~0.31 us with 16 CTAs; ncu: 60 % of the
+//       kernel's stall samples are the membar) costs per sweep what the relaunch costs per outer iteration
+//   whole flows, every level that fits on a cluster (FLOW2D_CLUSTER=2) against none (=0):
+//       16 pairs on 8 handles   C4 116.2 -> 117.5 Mpix/s device, 114.9 -> 116.8 end to end; C1b 84.1 -> 86.5, 81.7 -> 85.4
+//       one pair at a time      C4 14.98 -> 15.54 ms, C1b 7.14 -> 7.87 ms
+//       (only the levels up to 4 096 px, =1: batch within 1 % either way, one pair 1-3 % slower)
+//     i.e. one cluster of <= 16 CTAs for all 40 outer iterations takes far less SM time than 40 launches of 16-81 CTAs with
+//     their redundant rings -- which is what counts when other pairs' kernels wait for SMs -- but not less time
 //   pass mode: 1.5-3.3x slower than solve_small_pass / the tiled pass on every level -> off
-constexpr int kClusterWholeDefault = 1;
+//   => default (FLOW2D_CLUSTER unset): every level that fits a cluster when at least kClusterAutoHandles handles are alive
+//      on the device (frame pairs in flight at once: what counts is SM time), none for a lone handle (what counts is latency)
+constexpr int kClusterWholeDefault = -1;
 constexpr int kClusterPassDefault = 0;
+constexpr int kClusterAutoHandles = 4;
+int cluster_mode(const flow2d_handle* h) {
+  if (h->cluster_whole >= 0) return h->cluster_whole;
+  return live_handles(h->device) >= kClusterAutoHandles ? 2 : 0;
+}
 
 // Time of one barrier-to-barrier phase of the cluster kernel in us (a sweep, or one of the three set-up phases of an
 // outer iteration): the cluster barrier + the issue time of the CTA's warps.  Fitted to the measurements above
@@ -655,10 +674,11 @@ int run_solve(flow2d_handle* h, const LevelGeom& g, const float* u, const float*
   }
   // mid-size levels (up to 16 x 1024 pixels): one thread-block cluster, one thread per pixel, halos through distributed
   // shared memory, all outer iterations in the kernel
-  if (h->cluster_whole && !slabbed && !early && p->resident_levels == 0 && g.w >= 2 && g.h >= 2 &&
+  const int cmode = cluster_mode(h);
+  if (cmode && !slabbed && !early && p->resident_levels == 0 && g.w >= 2 && g.h >= 2 &&
       (long long)g.w * g.h <= (long long)kClusterMaxCtas * 1024) {
     const ClusterPlan cp = plan_cluster(h->cluster_active, g.w, g.h, h->cluster_compact || p->throughput_mode != 0);
-    if (cp.threads && (cp.threads <= 256 || h->cluster_whole >= 2)) {
+    if (cp.threads && (cp.threads <= 256 || cmode >= 2)) {
       a.du_in = a.dv_in = nullptr;
       a.phi_in = a.ksi_in = nullptr;
       a.du_out = du_a; a.dv_out = dv_a;
@@ -1383,16 +1403,20 @@ int flow2d_create(flow2d_handle** out, int device, size_t width, size_t height, 
     h->cluster_compact = std::getenv("FLOW2D_CLUSTER_COMPACT") != nullptr;
     int cmax = kClusterMaxCtas;
     if ((e = std::getenv("FLOW2D_CLUSTER_MAX")) != nullptr) cmax = std::atoi(e);
-    if (h->cluster_whole || h->cluster_pass)
+    if (h->cluster_whole != 0 || h->cluster_pass)
       for (int i = 0; i < 4; i++)
         for (int j = 0; j < 3; j++) h->cluster_active[i][j] = (2 << i) <= cmax ? solve_cluster_max_active(2 << i, 256 << j) : 0;
   }
+  if (device < kMaxCountedDevices) { ++g_live_handles[device]; h->counted = true; }
   *out = h;
   return FLOW2D_OK;
 }
 
+int flow2d_live_handles(int device) { return device >= 0 && device < kMaxCountedDevices ? g_live_handles[device].load() : 0; }
+
 int flow2d_destroy(flow2d_handle* h) {
   if (!h) return FLOW2D_OK;
+  if (h->counted) { --g_live_handles[h->device]; h->counted = false; }
   cudaSetDevice(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }

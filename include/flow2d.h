@@ -179,6 +179,11 @@ FLOW2D_API const char* flow2d_kernel_kind_name(int kind);
  * cell = {own, left, right, up, down offsets in a shared plane, push rank / offset (horizontal), push rank / offset
  * (vertical), gx, gy, has a cell, live, output, floats per shared plane}. */
 FLOW2D_API int flow2d_cluster_shape(int rw, int rh, int compact, int shape[5]);
+/* Handles of this process alive on `device`.  With FLOW2D_CLUSTER unset the scheduler reads it when a schedule is made
+ * (first call with a parameter set, or flow2d_prepare): from 4 handles on -- several frame pairs in flight on one GPU --
+ * every level of 1 025 .. 16 384 px runs on a cluster (least SM time: C4 batch +1.7 %, C1b batch +4.5 % end to end); a lone
+ * handle keeps one launch per outer iteration there (least latency).  Results are identical either way. */
+FLOW2D_API int flow2d_live_handles(int device);
 FLOW2D_API int flow2d_debug_cluster_cell(const int geom[5], const int level[7], int rank, int cluster, int thread, int cell[15]);
 
 /* The level schedule of one (containers, parameters) combination is captured into a CUDA graph on first use and replayed

@@ -1,9 +1,9 @@
 """The thread-block-cluster solve (csrc/solve_cluster.cu) against the oracle and against the other solve kernels, bit for bit.
 
 Whole-level mode: a level of up to 16 x 1024 pixels runs ALL outer iterations on one cluster of 2-16 CTAs (halos through
-distributed shared memory, barrier.cluster per sweep).  By default the scheduler uses it where a CTA's block fits 256
-threads (levels of 1 025 .. 4 096 pixels, profiles/r02/cluster_ab); FLOW2D_CLUSTER=2 extends it to every level that fits a
-cluster, which is what most tests here force.  Pass mode (opt-in, measured slower): a grid of clusters, one pass per launch,
+distributed shared memory, barrier.cluster per sweep).  By default the scheduler uses it when four or more handles are alive
+on the device (several frame pairs in flight: least SM time) and not for a lone handle (least latency; profiles/r02/cluster_ab);
+FLOW2D_CLUSTER=2 forces it for every level that fits a cluster, =1 where a CTA's block fits 256 threads, =0 never.  Pass mode (opt-in, measured slower): a grid of clusters, one pass per launch,
 128x64 / 128x128 regions.  The switches (FLOW2D_CLUSTER, FLOW2D_CLUSTER_PASS, ...) are read when a handle is created."""
 import contextlib
 import os
@@ -147,15 +147,39 @@ def test_cluster_redo_vote_is_cluster_wide(pkg, oracle, synth, torch_):
 
 
 @pytest.mark.parametrize("w,h,expect", [(30, 30, False), (36, 36, True), (64, 64, True), (60, 70, False), (91, 91, False)])
-def test_cluster_default_policy(pkg, oracle, synth, torch_, w, h, expect):
-    """no switch set: solve_tiny up to 1 024 px, the cluster up to 4 096 px (blocks of <= 256 threads), passes above"""
+def test_cluster_mode_1_policy(pkg, oracle, synth, torch_, w, h, expect):
+    """FLOW2D_CLUSTER=1: solve_tiny up to 1 024 px, the cluster up to 4 096 px (blocks of <= 256 threads), passes above"""
     f0, f1, u, v = _solve_inputs(synth, w, h, 77)
-    fl = _handle(pkg, w, h)
+    fl = _handle(pkg, w, h, FLOW2D_CLUSTER=1)
     p = pkg.default_params(outer=4, inner=5, alpha=20.0)
     du, dv, phi, ksi = _run_solve(torch_, fl, f0, f1, u, v, w, h, 1.2, 1.3, p)
     assert (fl.launch_counts().get("solve_cluster", 0) == 1) == expect, fl.launch_counts()
     edu, edv, ephi, eksi = oracle.solve_level(f0, f1, u, v, 1.2, 1.3, oracle.make_params(outer=4, inner=5, alpha=20.0))
     assert _eq(du, edu) and _eq(dv, edv) and _eq(phi, ephi) and _eq(ksi, eksi)
+
+
+def test_cluster_default_follows_the_handle_count(pkg, oracle, synth, torch_):
+    """FLOW2D_CLUSTER unset: from four handles alive on the device on (frame pairs in flight at once: SM time counts) a level
+    that fits a cluster runs on one; a lone handle keeps one launch per outer iteration (latency counts).  Same bits."""
+    w, h = 91, 82
+    f0, f1, u, v = _solve_inputs(synth, w, h, 31)
+    p = pkg.default_params(outer=5, inner=5, alpha=20.0)
+    edu, edv, ephi, eksi = oracle.solve_level(f0, f1, u, v, 1.2, 1.3, oracle.make_params(outer=5, inner=5, alpha=20.0))
+    fl = _handle(pkg, w, h)
+    extra = []
+    try:
+        while pkg.live_handles(0) < 4:
+            extra.append(_handle(pkg, 8, 8))
+        du, dv, phi, ksi = _run_solve(torch_, fl, f0, f1, u, v, w, h, 1.2, 1.3, p)
+        assert fl.launch_counts().get("solve_cluster", 0) == 1, fl.launch_counts()
+        assert _eq(du, edu) and _eq(dv, edv) and _eq(phi, ephi) and _eq(ksi, eksi)
+    finally:
+        for e in extra:
+            e.destroy()
+    if pkg.live_handles(0) < 4:  # (handles of earlier tests may still be waiting for the garbage collector)
+        du, dv, phi, ksi = _run_solve(torch_, fl, f0, f1, u, v, w, h, 1.2, 1.3, p)
+        assert fl.launch_counts().get("solve_cluster", 0) == 0 and fl.launch_counts().get("solve_small_pass", 0) == 5
+        assert _eq(du, edu) and _eq(dv, edv) and _eq(phi, ephi) and _eq(ksi, eksi)
 
 
 PASS_CASES = [(200, 150, 5), (333, 250, 3), (131, 67, 5), (260, 300, 7), (150, 140, 1)]
@@ -185,9 +209,14 @@ def test_cluster_full_flow_rub_pair(pkg, oracle, rub, env):
     h, w = f0.shape
     cfg = dict(levels=50, outer=10, inner=5, alpha=35.0, sigma=1.5, median=5)
     fl = _handle(pkg, w, h, **env)
+    extra = []
+    while not env and pkg.live_handles(0) < 4:  # no switch set: the cluster schedule needs four handles alive on the device
+        extra.append(_handle(pkg, 8, 8))
     u, v = fl.compute(f0, f1, pkg.default_params(**cfg))
     counts = fl.launch_counts()
-    assert counts.get("solve_cluster", 0) >= (10 if env else 5), counts
+    for e in extra:
+        e.destroy()
+    assert counts.get("solve_cluster", 0) >= 10, counts
     u2, v2 = fl.compute(f0, f1, pkg.default_params(**cfg))  # the replayed graph
     ou, ov = oracle.compute_flow(f0, f1, oracle.make_params(**cfg))
     assert _eq(u, ou) and _eq(v, ov)

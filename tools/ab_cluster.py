@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     "off": dict(FLOW2D_CLUSTER="0"),
-    "default": dict(),  # the cluster where a CTA's block fits 256 threads (levels of 1 025 .. 4 096 px)
+    "default": dict(),  # by the number of handles alive on the device: "whole" from 4 on, "off" below
+    "small": dict(FLOW2D_CLUSTER="1"),  # the cluster where a CTA's block fits 256 threads (levels of 1 025 .. 4 096 px)
     "whole": dict(FLOW2D_CLUSTER="2"),  # every level that fits a cluster (.. 16 384 px)
     "whole_compact": dict(FLOW2D_CLUSTER="2", FLOW2D_CLUSTER_COMPACT="1"),
     "whole_max8": dict(FLOW2D_CLUSTER="2", FLOW2D_CLUSTER_MAX="8"),
