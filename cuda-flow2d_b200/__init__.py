@@ -10,5 +10,5 @@ The directory name contains a hyphen; import it through ``flow2d_loader.load()``
 """
 from .binding import (  # noqa: F401
     GREY, GRADIENT, JACOBI, RED_BLACK, TERM_DEFAULT, TERM_GRADIENT, TERM_LOG_GRADIENT, TERM_COMBINED, Flow2D, Flow2DError, Params, build, default_params, level_geometry, level_table,
-    lib, lib_path, max_warp_level, version,
+    lib, lib_path, live_handles, max_warp_level, version,
 )

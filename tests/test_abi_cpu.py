@@ -45,6 +45,11 @@ def test_level_table_bit_exact_with_oracle(pkg, oracle, W, H, sf):
         assert hx.tobytes() == ohx.tobytes() and hy.tobytes() == ohy.tobytes()
 
 
+def test_live_handle_count_is_exported(pkg):
+    """flow2d_live_handles (the scheduler's "several pairs in flight?" signal) through the package"""
+    assert pkg.live_handles(0) >= 0 and pkg.live_handles(-1) == 0 and pkg.live_handles(1000) == 0
+
+
 def test_no_cpu_fallback(pkg):
     """Without a CUDA device the handle cannot be created: the product has no CPU path."""
     import torch
