@@ -21,6 +21,12 @@
 // n -> n-2) is folded into the neighbour addresses as in solve_tiny.  The "were the fast divisions safe" vote of
 // one_px_outer is cluster-wide (ClusterLink): all CTAs repeat an outer iteration or none does, so every CTA executes the
 // same number of cluster barriers.
+//
+// Measured on B200 (profiles/r02/cluster_ab/, solve_cluster_ncu_summary.txt): a barrier-to-barrier phase
+// takes 0.31 us (the barrier: MEMBAR.ALL.GPU for the pushed stores + UCGABAR + CCTL.IVALL) + 0.0155 us per warp of the
+// CTA, so a level takes about as long as with one solve_small_pass launch per outer iteration (<= 4 096 px) or longer --
+// but on <= 16 CTAs instead of 40 launches of 16-81: the scheduler uses it where SM time counts (flow2d_api.cu:
+// cluster_mode).  Next step: st.async + mbarrier::complete_tx between neighbours instead of the full barrier.
 #include "kernels.h"
 #include "solve_common.cuh"
 #include "solve_onepx.cuh"
